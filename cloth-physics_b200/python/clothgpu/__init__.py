@@ -1,0 +1,200 @@
+"""clothgpu — ctypes binding of libclothgpu.so (include/clothgpu.h).
+
+This is a test/bench harness over the C ABI, the same entry points the cgo shim of INTEGRATION.md
+binds.  It never computes anything itself and has no CPU path: if the CUDA library is missing or no
+B200 is visible, it raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (Counters, Desc, Frame, Info, default_desc, default_frame, grid_desc)  # noqa: F401
+from ._abi import *  # noqa: F401,F403  (constants)
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "csrc", "libclothgpu.so"))
+
+# Every symbol include/clothgpu.h declares.
+EXPORTS = [
+    "clothgpu_frame_default", "clothgpu_desc_default", "clothgpu_create", "clothgpu_reset",
+    "clothgpu_destroy", "clothgpu_step", "clothgpu_step_n", "clothgpu_step_each", "clothgpu_sync",
+    "clothgpu_get_info", "clothgpu_set_schedule", "clothgpu_read_state", "clothgpu_write_state",
+    "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_get_counters",
+    "clothgpu_halo_region", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
+    "clothgpu_last_error", "clothgpu_version",
+]
+
+_lib = None
+
+
+class ClothGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"clothgpu error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libclothgpu.so (built in-tree by __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ClothGpuError(_abi.ERR_NODEVICE,
+                                f"{LIB_PATH} not built; run python -c 'import __graft_entry__ as g; g.build()'")
+        L = C.CDLL(LIB_PATH)
+        dp, u8p, u32p = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+        vp = C.c_void_p
+        L.clothgpu_frame_default.argtypes = [C.POINTER(Frame)]
+        L.clothgpu_desc_default.argtypes = [C.POINTER(Desc)]
+        L.clothgpu_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
+        L.clothgpu_reset.argtypes = [vp, C.c_int32, C.c_int32]
+        L.clothgpu_destroy.argtypes = [vp]
+        L.clothgpu_destroy.restype = None
+        L.clothgpu_step.argtypes = [vp, C.POINTER(Frame)]
+        L.clothgpu_step_n.argtypes = [vp, C.POINTER(Frame), C.c_int32]
+        L.clothgpu_step_each.argtypes = [vp, C.POINTER(Frame), C.c_int32]
+        L.clothgpu_sync.argtypes = [vp]
+        L.clothgpu_get_info.argtypes = [vp, C.POINTER(Info)]
+        L.clothgpu_set_schedule.argtypes = [vp, C.c_int32]
+        L.clothgpu_read_state.argtypes = [vp, C.c_int32, dp, dp, dp, dp, u8p]
+        L.clothgpu_write_state.argtypes = [vp, C.c_int32, dp, dp, dp, dp, u8p]
+        L.clothgpu_read_masks.argtypes = [vp, C.c_int32, u32p, u32p, u32p, u32p, u32p]
+        L.clothgpu_read_segments_f32.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), u8p, u32p,
+                                                 C.c_size_t, C.POINTER(C.c_size_t)]
+        L.clothgpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
+        L.clothgpu_halo_region.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.clothgpu_set_stream.argtypes = [vp, vp]
+        L.clothgpu_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.clothgpu_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.clothgpu_last_error.restype = C.c_char_p
+        L.clothgpu_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ClothGpuError(rc, lib().clothgpu_last_error().decode())
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def frame_array(frames):
+    arr = (Frame * len(frames))()
+    for i, f in enumerate(frames):
+        C.memmove(C.byref(arr[i]), C.byref(f), C.sizeof(Frame))
+    return arr
+
+
+class Cloth:
+    """One device-resident cloth (or ensemble / strip): NewCloth + Init of the reference
+    (physics/cloth.go:31-81) behind the C ABI."""
+
+    def __init__(self, desc):
+        self._L = lib()
+        self._h = C.c_void_p()
+        _check(self._L.clothgpu_create(C.byref(desc), C.byref(self._h)))
+        self.desc = desc
+        self.info = Info()
+        _check(self._L.clothgpu_get_info(self._h, C.byref(self.info)))
+        self.nx, self.ny = self.info.nx, self.info.ny
+        self.rows, self.row0 = self.info.rows, self.info.row0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.clothgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # (*Cloth).Reset, physics/cloth.go:142-148
+    def reset(self, pos_x, pos_y):
+        _check(self._L.clothgpu_reset(self._h, pos_x, pos_y))
+
+    # physics half of (*Cloth).Update, physics/cloth.go:92-100
+    def step(self, frame):
+        _check(self._L.clothgpu_step(self._h, C.byref(frame)))
+
+    def step_n(self, frames):
+        arr = frames if isinstance(frames, C.Array) else frame_array(frames)
+        _check(self._L.clothgpu_step_n(self._h, arr, len(arr)))
+
+    def step_each(self, frames):
+        arr = frames if isinstance(frames, C.Array) else frame_array(frames)
+        _check(self._L.clothgpu_step_each(self._h, arr, len(arr)))
+
+    def sync(self):
+        _check(self._L.clothgpu_sync(self._h))
+
+    def set_schedule(self, s):
+        _check(self._L.clothgpu_set_schedule(self._h, s))
+
+    def set_stream(self, cuda_stream):
+        _check(self._L.clothgpu_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def read_state(self, cloth=0):
+        n = self.nx * self.rows
+        x, y, px, py = (np.empty(n, np.float64) for _ in range(4))
+        fl = np.empty(n, np.uint8)
+        _check(self._L.clothgpu_read_state(self._h, cloth, _p(x, C.c_double), _p(y, C.c_double),
+                                           _p(px, C.c_double), _p(py, C.c_double), _p(fl, C.c_uint8)))
+        return x, y, px, py, fl
+
+    def write_state(self, x=None, y=None, px=None, py=None, flags=None, cloth=0):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (x, y, px, py)]
+        fl = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        for a in arrs + [fl]:
+            assert a is None or a.size == self.nx * self.rows
+        _check(self._L.clothgpu_write_state(self._h, cloth, *[_p(a, C.c_double) for a in arrs],
+                                            _p(fl, C.c_uint8)))
+
+    def read_masks(self, cloth=0):
+        w = (self.nx * self.rows + 31) // 32
+        planes = [np.zeros(w, np.uint32) for _ in range(5)]
+        _check(self._L.clothgpu_read_masks(self._h, cloth, *[_p(a, C.c_uint32) for a in planes]))
+        return dict(zip(("pin", "active", "highlighted", "alive_h", "alive_v"), planes))
+
+    def read_segments(self, cloth=0, with_indices=False):
+        cap = 2 * self.nx * self.rows
+        xyxy = np.empty((cap, 4), np.float32)
+        hl = np.empty(cap, np.uint8)
+        idx = np.empty((cap, 2), np.uint32) if with_indices else None
+        n = C.c_size_t(0)
+        _check(self._L.clothgpu_read_segments_f32(self._h, cloth, _p(xyxy, C.c_float), _p(hl, C.c_uint8),
+                                                  _p(idx, C.c_uint32), cap, C.byref(n)))
+        if with_indices:
+            return xyxy[:n.value], hl[:n.value], idx[:n.value]
+        return xyxy[:n.value], hl[:n.value]
+
+    def counters(self):
+        c = Counters()
+        _check(self._L.clothgpu_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def halo_region(self, plane, which):
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        _check(self._L.clothgpu_halo_region(self._h, plane, which, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        _check(self._L.clothgpu_last_step_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(self._L.clothgpu_launch_count(self._h, C.byref(n)))
+        return n.value

@@ -1,0 +1,300 @@
+"""Known-answer tests pinning the C oracle to the reference's SOURCE TEXT (the reference ships no tests,
+so parity is otherwise unpinned).  Expected values are derived by hand from the cited Go lines."""
+import math
+
+import numpy as np
+import pytest
+
+from clothgpu import _abi
+from clothgpu._abi import (FLAG_ACTIVE, FLAG_ALIVE_H, FLAG_ALIVE_V, FLAG_HIGHLIGHT, FLAG_PIN, MOUSE_CTRL,
+                           MOUSE_DRAGGING, MOUSE_LEFT, MOUSE_RIGHT)
+
+
+def test_default_grid_census(oracle):
+    # main.go:149-166 + cloth.go:43-79: 171 x 36 particles, 12105 sticks, 11 pins at x%17==0 on row 0
+    c = oracle.OracleCloth(_abi.default_desc(), oracle.SEQ_FAITHFUL)
+    assert (c.nx, c.ny) == (171, 36)
+    assert c.slice_len == 12105
+    x, y, px, py, fl = c.read_state()
+    assert x.size == 6156
+    pins = np.flatnonzero(fl & FLAG_PIN)
+    assert list(pins) == list(range(0, 171, 17))
+    assert x.min() == 128 and x.max() == 1148 and y.min() == 164 and y.max() == 374
+    assert np.array_equal(x, px) and np.array_equal(y, py)
+    assert np.all(fl & FLAG_ACTIVE)
+    H = (fl & FLAG_ALIVE_H) != 0
+    V = (fl & FLAG_ALIVE_V) != 0
+    assert H.sum() == 6120 and V.sum() == 5985
+    assert not H.reshape(36, 171)[:, -1].any() and not V.reshape(36, 171)[-1, :].any()
+
+
+def test_reference_pin_rule_panics_below_10_columns(oracle):
+    # cloth.go:72: x % (clothX/10) divides by zero when Width/spacing < 10
+    d = _abi.grid_desc(9, 9, pin_rule=_abi.PIN_REFERENCE)
+    with pytest.raises(ValueError):
+        oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    oracle.OracleCloth(_abi.grid_desc(11, 4, pin_rule=_abi.PIN_REFERENCE), oracle.SEQ_FAITHFUL)
+
+
+def test_free_particle_first_frame(oracle):
+    # particle.go:151-162: y1 = y0 + 250 * (0.022*0.022); dt*dt is a run-time product, 1 ulp below 0.000484
+    d = _abi.grid_desc(11, 2, pin_rule=_abi.PIN_NONE)
+    c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    f = _abi.default_frame()
+    c.step(f)
+    x, y, px, py, fl = c.read_state()
+    dt2 = 0.022 * 0.022
+    assert dt2 == float.fromhex("0x1.fb82c2bd7f51ep-12") and dt2 != 0.000484
+    assert 250.0 * dt2 == 0.12099999999999998
+    assert y[0] == 164 + 250.0 * dt2
+    assert py[0] == 164.0 and x[0] == 128.0 and px[0] == 128.0
+
+
+def test_slider_float32_widening(oracle):
+    # particle.go:82: friction is float64(float32(0.98)) = 0.9800000190734863
+    d = _abi.grid_desc(11, 2, pin_rule=_abi.PIN_NONE)
+    c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    n = c.nx * c.ny
+    x, y, px, py, fl = c.read_state()
+    c.write_state(px=x - 1.0, py=y)           # velocity +1 in x
+    f = _abi.default_frame()
+    f.slider[_abi.SLIDER_GRAVITY] = 0.0
+    c.step(f)
+    x2, *_ = c.read_state()
+    assert x2[0] == x[0] + 1.0 * 0.9800000190734863
+    assert n == 22
+
+
+@pytest.mark.parametrize("d,expect", [(7.0, 0.05), (6.5, 0.013461538461538454), (12.0, 1.05), (150.0, 48.384)])
+def test_single_stick_offsets(oracle, d, expect):
+    # constraint.go:41-53: mul = ((L-d)/d)*0.35*(1-L/d); each endpoint moves |dx*mul| toward the other
+    (x1, y1, x2, y2), tore = oracle.stick_update(0.0, 0.0, d, 0.0)
+    assert not tore
+    assert x1 == pytest.approx(expect, rel=1e-12) and x2 == pytest.approx(d - expect, rel=1e-12)
+    assert y1 == 0.0 and y2 == 0.0
+    diff = (6.0 - d) / d
+    mul = diff * 0.35 * (1 - 6.0 / d)
+    assert x1 == 0.0 + (0.0 - d) * mul                     # exact operation order
+    assert x2 == d - (0.0 - d) * mul
+
+
+def test_stick_mul_d7_exact(oracle):
+    d = 7.0
+    mul = ((6.0 - d) / d) * 0.35 * (1 - 6.0 / d)
+    assert mul == -0.007142857142857144
+
+
+def test_stick_pinned_endpoint_moves_only_the_free_one(oracle):
+    # constraint.go:46-53: the offset is not doubled for the free endpoint
+    (x1, y1, x2, y2), _ = oracle.stick_update(0.0, 0.0, 7.0, 0.0, pin1=True)
+    assert x1 == 0.0 and x2 == pytest.approx(6.95, rel=1e-12)
+    (x1, y1, x2, y2), _ = oracle.stick_update(0.0, 0.0, 7.0, 0.0, pin2=True)
+    assert x1 == pytest.approx(0.05, rel=1e-12) and x2 == 7.0
+
+
+def test_stick_shorter_than_rest_is_untouched(oracle):
+    # constraint.go:30-32
+    (x1, y1, x2, y2), tore = oracle.stick_update(0.0, 0.0, 5.999, 0.0, dragging=True)
+    assert (x1, y1, x2, y2) == (0.0, 0.0, 5.999, 0.0) and not tore
+    # dist == length is NOT an early-out (strict <) but yields a zero correction
+    (x1, y1, x2, y2), tore = oracle.stick_update(0.0, 0.0, 6.0, 0.0)
+    assert (x1, x2) == (0.0, 6.0)
+
+
+def test_tear_needs_dragging_and_still_relaxes_once(oracle):
+    # constraint.go:35-39 then falls through to :41-53
+    (x1, _, x2, _), tore = oracle.stick_update(0.0, 0.0, 151.0, 0.0, dragging=False)
+    assert not tore and x1 > 0
+    (x1b, _, x2b, _), tore = oracle.stick_update(0.0, 0.0, 151.0, 0.0, dragging=True)
+    assert tore and (x1b, x2b) == (x1, x2)
+    # exactly 150 does not tear (strict >)
+    _, tore = oracle.stick_update(0.0, 0.0, 150.0, 0.0, dragging=True)
+    assert not tore
+
+
+def _row_of_sticks(oracle, n_sticks, mode):
+    # one row of n_sticks+1 particles => creation order H(1..n): stick k joins particles k, k+1
+    d = _abi.grid_desc(n_sticks + 1, 1, pin_rule=_abi.PIN_NONE, spacing=6, pos_x=0, pos_y=100)
+    return oracle.OracleCloth(d, mode)
+
+
+def _stretch(c, torn):
+    """Row cloth where exactly the sticks in `torn` are longer than 150."""
+    n = c.nx
+    xs = np.zeros(n)
+    for k in range(1, n):
+        xs[k] = xs[k - 1] + (400.0 if (k - 1) in torn else 6.0)
+    y = np.full(n, 100.0)
+    c.write_state(x=xs, y=y, px=xs, py=y)
+    f = _abi.default_frame()
+    f.slider[_abi.SLIDER_GRAVITY] = 0.0
+    f.win_w, f.win_h = 100000, 100000
+    f.buttons = MOUSE_DRAGGING
+    f.mouse_x = f.mouse_y = f.mouse_px = f.mouse_py = -1e6   # far away: no drag push
+    return f
+
+
+@pytest.mark.parametrize("torn,order,survivors_skipped", [
+    ({3}, [0, 1, 2, 3, 5, 6, 7, 8, 9, 9], {4}),
+    ({3, 5}, [0, 1, 2, 3, 5, 7, 8, 9, 9, 9], {4, 6}),
+])
+def test_slice_removal_artefact_visit_order(oracle, torn, order, survivors_skipped):
+    # constraint.go:57-64 mutates the slice cloth.go:96 is ranging over: the stick after a torn one is
+    # skipped that frame and the stale tail re-visits the last stick.
+    c = _row_of_sticks(oracle, 10, oracle.SEQ_FAITHFUL)
+    f = _stretch(c, torn)
+    c.step(f)
+    assert list(c.last_visit_order()) == order
+    assert c.slice_len == 10 - len(torn)
+    fl = c.read_state()[4]
+    alive = {k for k in range(10) if fl[k] & FLAG_ALIVE_H}
+    assert alive == set(range(10)) - torn
+
+
+def test_slice_removal_adjacent_tears_only_first_this_frame(oracle):
+    c = _row_of_sticks(oracle, 10, oracle.SEQ_FAITHFUL)
+    f = _stretch(c, {3, 4})
+    c.step(f)
+    assert c.torn_last == 1 and c.slice_len == 9
+    fl = c.read_state()[4]
+    assert not fl[3] & FLAG_ALIVE_H and fl[4] & FLAG_ALIVE_H
+    # masked mode has no artefact: both tear in the same frame, every stick visited exactly once
+    m = _row_of_sticks(oracle, 10, oracle.SEQ_MASKED)
+    f = _stretch(m, {3, 4})
+    m.step(f)
+    # (stick 5 also tears: relaxing stick 4 pulls particle 5 more than 150 px away from particle 6)
+    assert m.torn_last == 3 and m.relaxations == 10
+    fl = m.read_state()[4]
+    assert not fl[3] & FLAG_ALIVE_H and not fl[4] & FLAG_ALIVE_H
+
+
+def test_bounds_clamp_asymmetry(oracle):
+    # particle.go:164-178: x >= W clamps (>=) and zeroes x velocity; y > H clamps (strict >)
+    d = _abi.grid_desc(11, 1, pin_rule=_abi.PIN_NONE, pos_x=0, pos_y=0)
+    c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    n = c.nx
+    x = np.arange(n) * 6.0
+    y = np.zeros(n)
+    x[0], y[0] = 500.0, 820.0       # x lands exactly on W=500 -> clamps; y exactly on H -> not clamped (needs >)
+    x[1], y[1] = -5.0, 10.0         # x<0 clamps to 0
+    x[2], y[2] = 12.0, 830.0        # y>H clamps
+    c.write_state(x=x, y=y, px=x.copy(), py=y.copy())
+    f = _abi.default_frame()
+    f.slider[_abi.SLIDER_GRAVITY] = 0.0
+    f.win_w, f.win_h = 500, 820
+    # no stick interaction wanted: deactivate everything
+    fl = c.read_state()[4]
+    c.write_state(flags=(fl & ~np.uint8(FLAG_ACTIVE)))
+    c.step(f)
+    x2, y2, px2, py2, _ = c.read_state()
+    assert (x2[0], px2[0]) == (500.0, 500.0) and y2[0] == 820.0
+    assert (x2[1], px2[1]) == (0.0, 0.0)
+    assert (y2[2], py2[2]) == (820.0, 820.0)
+
+
+def test_pinned_particle_only_follows_window_offset(oracle):
+    # particle.go:85-92: pinned particles are never integrated, highlighted or hole-punched
+    d = _abi.grid_desc(11, 2, pin_rule=_abi.PIN_TOP_ROW, pos_x=100, pos_y=100)
+    c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    f = _abi.default_frame()
+    f.win_off_x, f.win_off_y = 3.5, -2.0
+    f.mouse_x, f.mouse_y = 100.0, 100.0
+    f.buttons = MOUSE_RIGHT
+    c.step(f)
+    x, y, px, py, fl = c.read_state()
+    assert x[0] == 103.5 and y[0] == 98.0 and px[0] == 100.0
+    assert fl[0] & FLAG_ACTIVE and not fl[0] & FLAG_HIGHLIGHT
+    # the free row below is inside the focus area (50): highlighted and deactivated
+    assert fl[11] & FLAG_HIGHLIGHT and not fl[11] & FLAG_ACTIVE
+
+
+def test_drag_force_accumulates_with_left_button_and_caps_at_slider_max(oracle):
+    # particle.go:96-99,184-189 and :108-125
+    d = _abi.grid_desc(11, 1, pin_rule=_abi.PIN_NONE, pos_x=0, pos_y=50)
+    f = _abi.default_frame()
+    f.slider[_abi.SLIDER_GRAVITY] = 0.0
+    f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 0.0, 50.0, -40.0, 45.0   # delta (40, 5) -> clamp x to 30
+    for force, drag in ((0.0, 2.0), (5.0, 7.0), (100.0, 15.0)):
+        c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+        fl = c.read_state()[4]
+        c.write_state(flags=fl & ~np.uint8(FLAG_ACTIVE))
+        f.buttons = MOUSE_LEFT | MOUSE_DRAGGING
+        f.mouse_force = force
+        c.step(f)
+        x, y, px, py, _ = c.read_state()
+        # px was set to x - 30*drag then Verlet: x' = x + (x - px)*fric ; px' = x
+        fr = float(np.float32(0.98))
+        assert x[0] == 0.0 + (0.0 - (0.0 - 30.0 * drag)) * fr + 0.0
+        assert y[0] == 50.0 + (50.0 - (50.0 - 5.0 * drag)) * fr + 0.0
+        assert x[3] == 18.0      # dist 18 >= tear-distance slider (15): untouched
+
+
+def test_ctrl_click_pins_but_still_integrates_this_frame(oracle):
+    # particle.go:128-130 sets pinX after the pin early-out of :85
+    d = _abi.grid_desc(11, 1, pin_rule=_abi.PIN_NONE, pos_x=0, pos_y=50)
+    c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    f = _abi.default_frame()
+    f.mouse_x, f.mouse_y = 6.0, 53.0       # dist 3 < ClothPinDist 4 from particle 1; particle 0 at dist 6.7
+    f.buttons = MOUSE_CTRL
+    c.step(f)
+    x, y, px, py, fl = c.read_state()
+    assert fl[1] & FLAG_PIN and not fl[0] & FLAG_PIN
+    assert y[1] > 50.0
+    y1 = y[1]
+    f.buttons = 0
+    c.step(f)
+    assert c.read_state()[1][1] == y1      # pinned now: no longer integrates
+
+
+def test_focus_area_clamped_to_30_120(oracle):
+    # particle.go:133-142
+    d = _abi.grid_desc(41, 1, pin_rule=_abi.PIN_NONE, pos_x=0, pos_y=0)
+    for scroll, radius in ((5.0, 30.0), (50.0, 50.0), (500.0, 120.0)):
+        c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+        f = _abi.default_frame()
+        f.scroll_y = scroll
+        f.mouse_x, f.mouse_y = 0.0, 0.0
+        c.step(f)
+        fl = c.read_state()[4]
+        hl = np.flatnonzero(fl & FLAG_HIGHLIGHT)
+        assert hl.max() == math.ceil(radius / 6.0) - 1
+
+
+def test_inactive_particles_keep_integrating_and_block_their_sticks(oracle):
+    # no isActive test anywhere in particle.update; cloth.go:97 skips sticks with an inactive endpoint
+    d = _abi.grid_desc(11, 2, pin_rule=_abi.PIN_NONE, pos_x=0, pos_y=0)
+    c = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL)
+    fl = c.read_state()[4]
+    fl[:] &= ~np.uint8(FLAG_ACTIVE)
+    c.write_state(flags=fl)
+    c.step(_abi.default_frame())
+    assert c.relaxations == 0
+    assert c.read_state()[1][0] == 250.0 * (0.022 * 0.022)
+
+
+def test_colour_mode_equals_sequential_when_sticks_are_disjoint(oracle):
+    # with one iteration and no shared particles between stretched sticks the order cannot matter
+    d = _abi.grid_desc(12, 1, pin_rule=_abi.PIN_NONE, pos_x=0, pos_y=10)
+    # even sticks 9 long (stretched), odd sticks 3 long (stay compressed -> early-out in any order)
+    xs = np.array([0, 9, 12, 21, 24, 33, 36, 45, 48, 57, 60, 69], float)
+    res = []
+    for mode in (oracle.SEQ_FAITHFUL, oracle.SEQ_MASKED, oracle.COLOUR):
+        c = oracle.OracleCloth(d, mode)
+        c.write_state(x=xs, px=xs)
+        f = _abi.default_frame()
+        f.slider[_abi.SLIDER_GRAVITY] = 0.0
+        c.step(f)
+        res.append(c.read_state()[0])
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+
+
+def test_openmp_threads_do_not_change_colour_mode_bits(oracle):
+    d = _abi.grid_desc(64, 48, pin_rule=_abi.PIN_TOP_ROW)
+    a, b = oracle.OracleCloth(d, oracle.COLOUR), oracle.OracleCloth(d, oracle.COLOUR)
+    f = _abi.default_frame(iterations=3)
+    for _ in range(20):
+        a.step(f, threads=1)
+        b.step(f, threads=4)
+    for u, v in zip(a.read_state(), b.read_state()):
+        assert np.array_equal(u, v)
+    assert a.relaxations == b.relaxations == 20 * 3 * (2 * 64 * 48 - 64 - 48)
