@@ -1,0 +1,350 @@
+// cloth_kernels.cuh — streaming schedule (one launch per pass) and the auxiliary kernels.
+//
+//   init_grid_kernel        <- (*Cloth).Init                          physics/cloth.go:42-81
+//   verlet_kernel           <- loop over particles                    physics/cloth.go:92-94
+//   relax_pass_kernel<C>    <- loop over sticks, one colour at a time physics/cloth.go:96-100
+//   count_kernel / pack_masks_kernel / segment kernels: read-back helpers
+//
+// The streaming schedule moves 64 B per stick relaxation through L2/HBM (2 endpoints x 16 B, read and
+// write) and is the correctness cross-check and the "unfused" companion figure of DESIGN.md; the
+// fused schedule in cloth_fused.cuh is the fast path.
+#pragma once
+#include "cloth_types.cuh"
+
+namespace clothgpu_impl {
+
+constexpr int kStreamThreads = 256;
+
+__device__ __forceinline__ unsigned long long block_sum_ull(unsigned long long v) {
+    // warp shuffle reduction, then one shared-memory hop across warps
+    __shared__ unsigned long long warp_part[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_part[w] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    if (w == 0) {
+        t = lane < (int)((blockDim.x + 31) >> 5) ? warp_part[lane] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;  // valid in thread 0
+}
+
+// (*Cloth).Init: rest grid, px = x, everything active, every existing stick alive, Init pins.
+template <typename T>
+__global__ void init_grid_kernel(Planes<T> P, Geom g, int ny, int spacing, int pos_x, int pos_y,
+                                 int pin_rule) {
+    const long long per_cloth = (long long)g.held_rows * g.pitch;
+    const long long total = per_cloth * g.ensemble;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / per_cloth);
+        const long long r = i - (long long)e * per_cloth;
+        const int ly = (int)(r / g.pitch), cx = (int)(r - (long long)ly * g.pitch);
+        const int gy = g.held_row0 + ly;
+        const long long at = (long long)e * g.cloth_stride + r;
+        T x = T(0), y = T(0);
+        uint8_t fl = 0;
+        if (cx < g.nx) {
+            x = (T)(pos_x + cx * spacing);  // cloth.go:53-56: integer arithmetic, then float64()
+            y = (T)(pos_y + gy * spacing);
+            fl = CLOTHGPU_FLAG_ACTIVE;
+            if (cx + 1 < g.nx) fl |= CLOTHGPU_FLAG_ALIVE_H;  // cloth.go:66-70
+            if (gy + 1 < ny) fl |= CLOTHGPU_FLAG_ALIVE_V;    // cloth.go:61-65
+            if (gy == 0) {                                   // cloth.go:72-75
+                if (pin_rule == CLOTHGPU_PIN_REFERENCE) {
+                    if (cx % ((g.nx - 1) / 10) == 0) fl |= CLOTHGPU_FLAG_PIN;
+                } else if (pin_rule == CLOTHGPU_PIN_TOP_ROW) {
+                    fl |= CLOTHGPU_FLAG_PIN;
+                }
+            }
+        }
+        P.x[at] = x;
+        P.y[at] = y;
+        P.px[at] = x;
+        P.py[at] = y;
+        P.fl[at] = fl;
+    }
+}
+
+// Loop over particles (physics/cloth.go:92-94), in place.  One thread per particle of the held rows.
+// `per_cloth` (optional) holds one FrameU per cloth of an ensemble; otherwise every cloth uses u0.
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads)
+    verlet_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth) {
+    const int e = blockIdx.y;
+    FrameU<T> u = u0;
+    if (per_cloth) u = per_cloth[e];
+    const long long n = (long long)g.held_rows * g.pitch;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = (int)(i % g.pitch);
+    if (cx >= g.nx) return;
+    const long long at = (long long)e * g.cloth_stride + i;
+    T x = P.x[at], y = P.y[at], px = P.px[at], py = P.py[at];
+    uint32_t fl = P.fl[at];
+    particle_update(x, y, px, py, fl, u);
+    P.x[at] = x;
+    P.y[at] = y;
+    P.px[at] = px;
+    P.py[at] = py;
+    P.fl[at] = (uint8_t)fl;
+}
+
+// One colour pass over the held rows, in place.  COLOUR: 0 H-even, 1 H-odd, 2 V-even, 3 V-odd
+// (parity of the head particle's global column / row).  Each colour is a perfect matching, so the
+// threads of one pass never touch the same particle.
+template <typename T, int COLOUR>
+__global__ void __launch_bounds__(kStreamThreads)
+    relax_pass_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth,
+                      DevCounters* ctr) {
+    const int e = blockIdx.y;
+    FrameU<T> u = u0;
+    if (per_cloth) u = per_cloth[e];
+    constexpr bool kVertical = COLOUR >= 2;
+    constexpr int kOdd = COLOUR & 1;
+    unsigned long long visits = 0, torn = 0;
+    long long head = -1, tail = -1;
+    bool owned = false;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (!kVertical) {
+        const int per_row = max(1, g.nx / 2);  // upper bound on sticks of one colour per row
+        const int ly = (int)(i / per_row), k = (int)(i % per_row);
+        const int c = 2 * k + kOdd;
+        if (ly < g.held_rows && c + 1 < g.nx) {
+            head = (long long)ly * g.pitch + c;
+            tail = head + 1;
+            const int gy = g.held_row0 + ly;
+            owned = gy >= g.own_row0 && gy < g.own_row0 + g.own_rows;
+        }
+    } else {
+        // first held row with the wanted global parity
+        const int first = ((g.held_row0 & 1) == kOdd) ? 0 : 1;
+        const int j = (int)(i / g.nx), c = (int)(i % g.nx);
+        const int ly = first + 2 * j;
+        if (ly + 1 < g.held_rows) {
+            head = (long long)ly * g.pitch + c;
+            tail = head + g.pitch;
+            const int gy = g.held_row0 + ly;
+            owned = gy >= g.own_row0 && gy < g.own_row0 + g.own_rows;
+        }
+    }
+    if (head >= 0) {
+        const long long base = (long long)e * g.cloth_stride;
+        head += base;
+        tail += base;
+        const uint32_t f1 = P.fl[head], f2 = P.fl[tail];
+        const uint32_t alive_bit = kVertical ? CLOTHGPU_FLAG_ALIVE_V : CLOTHGPU_FLAG_ALIVE_H;
+        if ((f1 & alive_bit) && (f1 & f2 & CLOTHGPU_FLAG_ACTIVE)) {  // cloth.go:97
+            T x1 = P.x[head], y1 = P.y[head], x2 = P.x[tail], y2 = P.y[tail];
+            const bool tore = stick_relax(x1, y1, x2, y2, (f1 & CLOTHGPU_FLAG_PIN) != 0,
+                                          (f2 & CLOTHGPU_FLAG_PIN) != 0, u);
+            P.x[head] = x1;
+            P.y[head] = y1;
+            P.x[tail] = x2;
+            P.y[tail] = y2;
+            if (tore) P.fl[head] = (uint8_t)(f1 & ~alive_bit);  // tear = clear the alive bit in place
+            if (owned) {
+                visits = 1;
+                torn = tore ? 1 : 0;
+            }
+        }
+    }
+    const unsigned long long v = block_sum_ull(visits);
+    const unsigned long long t = block_sum_ull(torn);
+    if (threadIdx.x == 0) {
+        if (v) atomicAdd(&ctr->relaxations, v);
+        if (t) {
+            atomicAdd(&ctr->torn_total, t);
+            atomicAdd(&ctr->torn_last, t);
+        }
+    }
+}
+
+// Census of the owned rows: {live sticks, alive sticks, pinned, inactive, highlighted}.
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads)
+    count_kernel(Planes<T> P, Geom g, unsigned long long* out5) {
+    const int e = blockIdx.y;
+    const long long n = (long long)g.own_rows * g.pitch;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    unsigned long long live = 0, alive = 0, pinned = 0, inactive = 0, hl = 0;
+    if (i < n) {
+        const int cx = (int)(i % g.pitch);
+        if (cx < g.nx) {
+            const long long at = (long long)e * g.cloth_stride +
+                                 (long long)(g.own_row0 - g.held_row0) * g.pitch + i;
+            const uint32_t f = P.fl[at];
+            pinned = (f & CLOTHGPU_FLAG_PIN) ? 1 : 0;
+            inactive = (f & CLOTHGPU_FLAG_ACTIVE) ? 0 : 1;
+            hl = (f & CLOTHGPU_FLAG_HIGHLIGHT) ? 1 : 0;
+            if (f & CLOTHGPU_FLAG_ALIVE_H) {
+                alive++;
+                if ((f & P.fl[at + 1]) & CLOTHGPU_FLAG_ACTIVE) live++;
+            }
+            if (f & CLOTHGPU_FLAG_ALIVE_V) {
+                alive++;
+                if ((f & P.fl[at + g.pitch]) & CLOTHGPU_FLAG_ACTIVE) live++;
+            }
+        }
+    }
+    unsigned long long v[5] = {live, alive, pinned, inactive, hl};
+    for (int k = 0; k < 5; k++) {
+        const unsigned long long s = block_sum_ull(v[k]);
+        if (threadIdx.x == 0 && s) atomicAdd(&out5[k], s);
+    }
+}
+
+// Flag byte -> five 1-bit planes over the owned particles in row-major order WITHOUT row padding
+// (bit i = particle i = x + y*nx), assembled with warp ballots.
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads)
+    pack_masks_kernel(Planes<T> P, Geom g, int cloth, uint32_t* __restrict__ out, long long words) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // particle index
+    const long long n = (long long)g.own_rows * g.nx;
+    uint32_t f = 0;
+    if (i < n) {
+        const int ly = (int)(i / g.nx), cx = (int)(i % g.nx);
+        f = P.fl[(long long)cloth * g.cloth_stride +
+                 (long long)(g.own_row0 - g.held_row0 + ly) * g.pitch + cx];
+    }
+    const long long w = i >> 5;
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (f >> b) & 1u);
+        if ((threadIdx.x & 31) == 0 && w < words) out[(long long)b * words + w] = m;
+    }
+}
+
+// ---- live-stick list (render export; physics/cloth.go:108-114, 126-134) ------------------------------
+// Sticks are listed in the order Cloth.Init created them (physics/cloth.go:61-70): by TAIL particle in
+// row-major order, the vertical stick (from the particle above) before the horizontal one (from the
+// particle to the left).  A stick is listed when it is still in the slice and both endpoints are
+// active.  Three launches: per-block counts, a one-block exclusive scan, ballot-ranked scatter.
+template <typename T>
+__device__ __forceinline__ int tail_sticks(const Planes<T>& P, const Geom& g, long long base, int ly,
+                                           int cx, bool& v_live, bool& h_live) {
+    // ly counts owned rows; the row above the first owned row is a ghost row (strip) or absent
+    v_live = h_live = false;
+    const long long at = base + (long long)(g.own_row0 - g.held_row0 + ly) * g.pitch + cx;
+    const uint32_t f = P.fl[at];
+    if (!(f & CLOTHGPU_FLAG_ACTIVE)) return 0;
+    if (g.own_row0 + ly > g.held_row0) {
+        const uint32_t fu = P.fl[at - g.pitch];
+        v_live = (fu & CLOTHGPU_FLAG_ALIVE_V) && (fu & CLOTHGPU_FLAG_ACTIVE);
+    }
+    if (cx > 0) {
+        const uint32_t fw = P.fl[at - 1];
+        h_live = (fw & CLOTHGPU_FLAG_ALIVE_H) && (fw & CLOTHGPU_FLAG_ACTIVE);
+    }
+    return (int)v_live + (int)h_live;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads)
+    segment_count_kernel(Planes<T> P, Geom g, int cloth, unsigned int* __restrict__ block_counts) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)g.own_rows * g.nx;
+    unsigned long long c = 0;
+    if (i < n) {
+        bool v, h;
+        c = tail_sticks(P, g, (long long)cloth * g.cloth_stride, (int)(i / g.nx), (int)(i % g.nx), v, h);
+    }
+    const unsigned long long s = block_sum_ull(c);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned int)s;
+}
+
+// exclusive scan of block_counts in place (single block); total -> *total_out
+__global__ void __launch_bounds__(1024)
+    segment_scan_kernel(unsigned int* __restrict__ block_counts, int n,
+                        unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n ? block_counts[i] : 0;
+        unsigned long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long t = warp_tot[lane];
+            unsigned long long ti = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long q = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += q;
+            }
+            warp_tot[lane] = ti - t;  // exclusive across warps
+        }
+        __syncthreads();
+        const unsigned long long excl = carry + warp_tot[w] + inc - v;
+        if (i < n) block_counts[i] = (unsigned int)excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads)
+    segment_write_kernel(Planes<T> P, Geom g, int cloth, const unsigned int* __restrict__ block_offsets,
+                         float4* __restrict__ xyxy, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
+                         unsigned long long cap) {
+    __shared__ unsigned int warp_base[kStreamThreads / 32];
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)g.own_rows * g.nx;
+    const long long base = (long long)cloth * g.cloth_stride;
+    bool v = false, h = false;
+    int ly = 0, cx = 0;
+    if (i < n) {
+        ly = (int)(i / g.nx);
+        cx = (int)(i % g.nx);
+        tail_sticks(P, g, base, ly, cx, v, h);
+    }
+    // warp-ballot ranking: within a warp, lane l's sticks come after all sticks of lanes < l
+    const uint32_t bv = __ballot_sync(0xffffffffu, v), bh = __ballot_sync(0xffffffffu, h);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t below = (1u << lane) - 1u;
+    const unsigned int rank = __popc(bv & below) + __popc(bh & below);
+    const unsigned int wtot = __popc(bv) + __popc(bh);
+    if (lane == 0) warp_base[w] = wtot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int k = 0; k < kStreamThreads / 32; k++) {
+            const unsigned int t = warp_base[k];
+            warp_base[k] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    unsigned long long o = (unsigned long long)block_offsets[blockIdx.x] + warp_base[w] + rank;
+    if (!(v || h)) return;
+    const long long at = base + (long long)(g.own_row0 - g.held_row0 + ly) * g.pitch + cx;
+    const float x2 = (float)P.x[at], y2 = (float)P.y[at];  // cloth.go:110-111: float32(c.p2.x)
+    const bool hl2 = (P.fl[at] & CLOTHGPU_FLAG_HIGHLIGHT) != 0;
+    const unsigned int tail_i = (unsigned int)((long long)ly * g.nx + cx);
+    if (v) {
+        if (o < cap) {
+            xyxy[o] = make_float4((float)P.x[at - g.pitch], (float)P.y[at - g.pitch], x2, y2);
+            hl[o] = hl2 && (P.fl[at - g.pitch] & CLOTHGPU_FLAG_HIGHLIGHT);  // cloth.go:127-128
+            if (idx) idx[o] = make_uint2(tail_i - g.nx, tail_i);
+        }
+        o++;
+    }
+    if (h && o < cap) {
+        xyxy[o] = make_float4((float)P.x[at - 1], (float)P.y[at - 1], x2, y2);
+        hl[o] = hl2 && (P.fl[at - 1] & CLOTHGPU_FLAG_HIGHLIGHT);
+        if (idx) idx[o] = make_uint2(tail_i - 1, tail_i);
+    }
+}
+
+}  // namespace clothgpu_impl

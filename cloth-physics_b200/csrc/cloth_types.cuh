@@ -1,0 +1,138 @@
+// cloth_types.cuh — device-side data layout and the two per-element update rules.
+//
+// State lives as structure-of-arrays planes in HBM: x, y, px, py (binary64, or binary32 in the
+// optional F32 mode) plus one flag byte per particle (CLOTHGPU_FLAG_* of include/clothgpu.h).
+// Rows are `pitch` elements apart (pitch = nx rounded up to 16 elements, so every row starts on a
+// 128-byte line and even columns are 16-byte aligned for 128-bit vector access).
+//
+// The arithmetic below restates physics/particle.go:75-181 and physics/constraint.go:25-54 of the
+// reference.  It is compiled with -fmad=false: every product and sum is rounded separately, exactly
+// as the Go compiler emits for amd64.  CUDA's binary64 `/` and sqrt() are IEEE round-to-nearest.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/clothgpu.h"
+
+namespace clothgpu_impl {
+
+template <typename T>
+struct Planes {
+    T* x;
+    T* y;
+    T* px;
+    T* py;
+    uint8_t* fl;
+};
+
+// Geometry of what one handle holds.  "Held" rows = owned rows plus ghost rows (strips only).
+struct Geom {
+    int nx;            // particles per row of the cloth
+    int pitch;         // elements between rows
+    int held_row0;     // global index of the first held row
+    int held_rows;     // rows held
+    int own_row0;      // global index of the first owned row
+    int own_rows;      // rows owned
+    long long cloth_stride;  // elements between consecutive cloths of an ensemble (per plane)
+    int ensemble;
+};
+
+// Frame-uniform values, folded once per frame on the host in the reference's operation order
+// (frame_fold.h).  The reference re-derives all of them per particle (physics/particle.go:78-83,
+// 96-99, 109-122, 133-138, 152-155); they do not depend on the particle.
+template <typename T>
+struct FrameU {
+    T mx, my;          // Mouse.x, Mouse.y
+    T push_x, push_y;  // clamp(m - mprev, +-stiffness) * dragForce      particle.go:109-125
+    T s_drag;          // dist < tearDistance  <=>  dist^2 sum < s_drag  (exact, see frame_fold.h)
+    T s_pin;           // dist < ClothPinDist(4)
+    T s_focus;         // dist < focusArea
+    T fric;            // slider "friction" widened from float32       particle.go:82
+    T gx, gy;          // posX, posY = v * (dt*dt)                      particle.go:152-155
+    T W, H;            // window size as REAL                           particle.go:164,172
+    T off_x, off_y;    // hud.WinOffsetX/Y                              particle.go:89-90
+    T L;               // rest length = REAL(spacing)                   cloth.go:63,68
+    T s_rest;          // dist < L  <=>  dist^2 sum < s_rest            constraint.go:30
+    T tear_len;        // 150                                           constraint.go:36
+    T gain;            // 0.35                                          constraint.go:42
+    uint32_t buttons;  // CLOTHGPU_MOUSE_*
+    int iterations;
+};
+
+// Device-side counters accumulated by the step kernels (the rest are computed on demand).
+struct DevCounters {
+    unsigned long long relaxations;  // stick visits
+    unsigned long long torn_total;
+    unsigned long long torn_last;    // reset before each frame
+};
+
+// (*particle).update, physics/particle.go:75-181.  `fl` is the particle's flag byte.
+template <typename T>
+__device__ __forceinline__ void particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,
+                                                const FrameU<T>& u) {
+    fl &= ~(uint32_t)CLOTHGPU_FLAG_HIGHLIGHT;  // :76
+    if (fl & CLOTHGPU_FLAG_PIN) {              // :85-92
+        x += u.off_x;
+        y += u.off_y;
+        return;
+    }
+    const T dx = x - u.mx;  // :104-106; the sqrt is folded into the thresholds s_*
+    const T dy = y - u.my;
+    const T s = dx * dx + dy * dy;
+    if ((u.buttons & CLOTHGPU_MOUSE_DRAGGING) && s < u.s_drag) {  // :108-125
+        px = x - u.push_x;
+        py = y - u.push_y;
+    }
+    if ((u.buttons & CLOTHGPU_MOUSE_CTRL) && s < u.s_pin) fl |= CLOTHGPU_FLAG_PIN;  // :128-130
+    if (s < u.s_focus) {                                                            // :140-149
+        fl |= CLOTHGPU_FLAG_HIGHLIGHT;
+        if (u.buttons & CLOTHGPU_MOUSE_RIGHT) fl &= ~(uint32_t)CLOTHGPU_FLAG_ACTIVE;
+    }
+    const T ox = x, oy = y;              // :151
+    x = x + (x - px) * u.fric + u.gx;    // :159
+    y = y + (y - py) * u.fric + u.gy;    // :160
+    px = ox;                             // :162
+    py = oy;
+    if (x >= u.W) {  // :164-170
+        x = u.W;
+        px = x;
+    } else if (x < T(0)) {
+        x = T(0);
+        px = x;
+    }
+    if (y > u.H) {  // :172-178
+        y = u.H;
+        py = y;
+    } else if (y < T(0)) {
+        y = T(0);
+        py = y;
+    }
+}
+
+// (*constraint).Update, physics/constraint.go:25-54, on a stick known to be live (still in the
+// slice, both endpoints active: physics/cloth.go:97).  Returns true when the stick tears; it is still
+// relaxed on that visit because the Go code falls through after removeConstraint (:37 -> :41).
+template <typename T>
+__device__ __forceinline__ bool stick_relax(T& x1, T& y1, T& x2, T& y2, bool pin1, bool pin2,
+                                            const FrameU<T>& u) {
+    const T dx = x1 - x2;  // :26-28
+    const T dy = y1 - y2;
+    const T s = dx * dx + dy * dy;
+    if (s < u.s_rest) return false;  // :30-32  (dist < length, decided on s exactly)
+    const T dist = sqrt(s);
+    const bool tore = (u.buttons & CLOTHGPU_MOUSE_DRAGGING) && dist > u.tear_len;  // :35-39
+    const T diff = (u.L - dist) / dist;                   // :41
+    const T mul = diff * u.gain * (T(1) - u.L / dist);    // :42
+    const T ox = dx * mul, oy = dy * mul;                 // :44
+    if (!pin1) {                                          // :46-49
+        x1 += ox;
+        y1 += oy;
+    }
+    if (!pin2) {  // :50-53
+        x2 -= ox;
+        y2 -= oy;
+    }
+    return tore;
+}
+
+}  // namespace clothgpu_impl

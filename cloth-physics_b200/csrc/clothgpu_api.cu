@@ -1,0 +1,772 @@
+// clothgpu_api.cu — implementation of include/clothgpu.h: handle management, per-frame scheduling of
+// the sm_100a kernels, read-back.  No CPU compute path exists here: every physics result comes from
+// the kernels in cloth_kernels.cuh / cloth_fused.cuh.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cloth_fused.cuh"
+#include "cloth_kernels.cuh"
+#include "frame_fold.h"
+
+using namespace clothgpu_impl;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(CLOTHGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+constexpr int kMaxSweepsPerLaunch = 8;  // halo 16; larger K is split into several launches
+
+}  // namespace
+
+struct clothgpu {
+    clothgpu_desc desc{};
+    Geom g{};
+    int ny = 0;
+    int ghost = 0;
+    int precision = CLOTHGPU_F64;
+    int device = 0;
+    int sm_count = 0;
+    int schedule = CLOTHGPU_SCHED_AUTO;
+    size_t elem = 8;
+    size_t plane_elems = 0;  // per plane, all cloths
+    // double-buffered planes: positions+flags flip every launch, previous positions every frame
+    void* X[2] = {nullptr, nullptr};
+    void* Y[2] = {nullptr, nullptr};
+    void* PX[2] = {nullptr, nullptr};
+    void* PY[2] = {nullptr, nullptr};
+    uint8_t* FL[2] = {nullptr, nullptr};
+    int cur_pos = 0, cur_prev = 0;
+    DevCounters* ctr = nullptr;        // [0] totals; torn slots live in torn2
+    unsigned long long* torn2 = nullptr;  // torn count of even / odd frames
+    unsigned long long* census = nullptr; // 5 values
+    void* frames_dev = nullptr;        // per-cloth FrameU array (ensemble input)
+    void* frames_host = nullptr;       // pinned staging for the above
+    cudaEvent_t frames_copied = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t frames = 0;
+    uint64_t launches = 0;
+    int forced_tile_rows = 0;
+    int sweeps_per_launch = kMaxSweepsPerLaunch;
+    // scratch for segment export
+    unsigned int* seg_counts = nullptr;
+    size_t seg_counts_cap = 0;
+    void* seg_out = nullptr;
+    size_t seg_out_cap = 0;
+    unsigned long long* seg_total = nullptr;
+};
+
+namespace {
+
+template <typename T>
+Planes<T> planes(clothgpu* c, int pos, int prev) {
+    Planes<T> p;
+    p.x = (T*)c->X[pos];
+    p.y = (T*)c->Y[pos];
+    p.px = (T*)c->PX[prev];
+    p.py = (T*)c->PY[prev];
+    p.fl = c->FL[pos];
+    return p;
+}
+
+// Tile-row choice for the fused kernel: the largest tile that fits shared memory minimises halo
+// overhead, but the number of tiles should fill whole waves of SMs; cost ~ waves * tile rows.
+template <typename T>
+FusedPlan make_plan(const clothgpu* c, int K, int do_verlet) {
+    const Geom& g = c->g;
+    FusedPlan pl{};
+    pl.K = K;
+    pl.h = 2 * K;
+    pl.do_verlet = do_verlet;
+    const int h = pl.h, TW = kFusedTW;
+    // columns
+    if (g.nx <= TW) {
+        pl.tiles_x = 1;
+        pl.first_w = TW;
+        pl.mid_w = TW - 2 * h;
+    } else {
+        pl.first_w = TW - h;
+        pl.mid_w = TW - 2 * h;
+        pl.tiles_x = 1 + (g.nx - pl.first_w + pl.mid_w - 1) / pl.mid_w;
+    }
+    // rows
+    const int above = g.own_row0 - g.held_row0;
+    const int below = (g.held_row0 + g.held_rows) - (g.own_row0 + g.own_rows);
+    pl.top_margin = std::min(h, above);
+    const int bottom_margin = std::min(h, below);
+    const size_t smem_max = 227 * 1024;
+    int th_max = 2;
+    while (fused_smem_bytes<T>(th_max + 2) <= smem_max) th_max += 2;
+    const int th_min = 2 * h + 2;
+    auto tiles_y_for = [&](int TH, int* first_h) {
+        if (pl.top_margin + g.own_rows + bottom_margin <= TH) {
+            *first_h = g.own_rows;
+            return 1;
+        }
+        *first_h = TH - pl.top_margin - h;
+        const int mid = TH - 2 * h;
+        return 1 + (g.own_rows - *first_h + mid - 1) / mid;
+    };
+    int best_th = th_max;
+    if (c->forced_tile_rows >= th_min && c->forced_tile_rows <= th_max) {
+        best_th = c->forced_tile_rows & ~1;
+    } else {
+        double best_cost = 1e300;
+        for (int TH = th_max; TH >= th_min; TH -= 2) {
+            int fh;
+            const int ty = tiles_y_for(TH, &fh);
+            const long long tiles = (long long)ty * pl.tiles_x * g.ensemble;
+            const long long waves = (tiles + c->sm_count - 1) / c->sm_count;
+            // a tile costs ~ its rows (+ a little fixed overhead); small tiles may co-reside 2 per SM
+            const double cost = (double)waves * (TH + 6);
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                best_th = TH;
+            }
+            if (pl.top_margin + g.own_rows + bottom_margin > TH && TH - 2 * h < 2) break;
+        }
+    }
+    pl.TH = best_th;
+    pl.tiles_y = tiles_y_for(best_th, &pl.first_h);
+    pl.mid_h = best_th - 2 * h;
+    return pl;
+}
+
+template <typename T>
+int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, int K, int do_verlet) {
+    // The frame block travels by value in the kernel parameters; per-cloth blocks (ensembles) through
+    // device memory.
+    FusedPlan pl = make_plan<T>(c, K, do_verlet);
+    const size_t smem = fused_smem_bytes<T>(pl.TH);
+    CU_TRY(cudaFuncSetAttribute(fused_frame_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(227 * 1024)));
+    const int nxt = c->cur_pos ^ 1;
+    Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
+    Planes<T> out = planes<T>(c, nxt, do_verlet ? (c->cur_prev ^ 1) : c->cur_prev);
+    dim3 grid(pl.tiles_x, pl.tiles_y, c->g.ensemble);
+    fused_frame_kernel<T><<<grid, kFusedThreads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    c->cur_pos = nxt;
+    if (do_verlet) c->cur_prev ^= 1;
+    return CLOTHGPU_OK;
+}
+
+template <typename T>
+int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
+    const Geom& g = c->g;
+    Planes<T> P = planes<T>(c, c->cur_pos, c->cur_prev);
+    const FrameU<T>* fr = per_cloth;
+    const long long np = (long long)g.held_rows * g.pitch;
+    dim3 gp((unsigned)((np + kStreamThreads - 1) / kStreamThreads), g.ensemble);
+    verlet_kernel<T><<<gp, kStreamThreads, 0, c->stream>>>(P, g, u, fr);
+    c->launches++;
+    const long long nh = (long long)g.held_rows * std::max(1, g.nx / 2);
+    const long long nv = (long long)((g.held_rows + 1) / 2) * g.nx;
+    dim3 gh((unsigned)((nh + kStreamThreads - 1) / kStreamThreads), g.ensemble);
+    dim3 gv((unsigned)((nv + kStreamThreads - 1) / kStreamThreads), g.ensemble);
+    for (int it = 0; it < u.iterations; ++it) {
+        relax_pass_kernel<T, 0><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+        relax_pass_kernel<T, 1><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+        relax_pass_kernel<T, 2><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+        relax_pass_kernel<T, 3><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+        c->launches += 4;
+    }
+    CU_TRY(cudaGetLastError());
+    return CLOTHGPU_OK;
+}
+
+}  // namespace
+
+// torn_last bookkeeping: frame f accumulates into ctr->torn_last; it is zeroed (stream ordered)
+// before the frame's first launch.
+namespace {
+
+template <typename T>
+int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_cloth) {
+    // validate first
+    for (int i = 0; i < count; ++i) {
+        const clothgpu_frame& f = frames[i];
+        const int K = f.iterations < 1 ? 1 : f.iterations;
+        if (c->desc.strip_rows > 0 && 2 * K > c->ghost)
+            return fail(CLOTHGPU_ERR_INVALID, "iterations=%d needs %d ghost rows, handle has %d (raise desc.max_iterations)",
+                        K, 2 * K, c->ghost);
+        if (per_cloth && K != (frames[0].iterations < 1 ? 1 : frames[0].iterations))
+            return fail(CLOTHGPU_ERR_INVALID, "per-cloth frames must share `iterations`");
+    }
+    const FrameU<T>* dev_frames = nullptr;
+    FrameU<T> u0 = fold_frame<T>(frames[0], c->desc.spacing);
+    if (per_cloth) {
+        // wait until the previous upload has left the pinned staging buffer
+        CU_TRY(cudaEventSynchronize(c->frames_copied));
+        FrameU<T>* st = (FrameU<T>*)c->frames_host;
+        for (int e = 0; e < count; ++e) st[e] = fold_frame<T>(frames[e], c->desc.spacing);
+        CU_TRY(cudaMemcpyAsync(c->frames_dev, st, sizeof(FrameU<T>) * count, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaEventRecord(c->frames_copied, c->stream));
+        dev_frames = (const FrameU<T>*)c->frames_dev;
+    }
+    CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, sizeof(unsigned long long), c->stream));
+    int sched = c->schedule == CLOTHGPU_SCHED_AUTO ? CLOTHGPU_SCHED_FUSED : c->schedule;
+    int rc;
+    if (sched == CLOTHGPU_SCHED_STREAMING) {
+        rc = launch_streaming<T>(c, u0, dev_frames);
+    } else {
+        int left = u0.iterations, first = 1;
+        rc = CLOTHGPU_OK;
+        while (left > 0 && rc == CLOTHGPU_OK) {
+            const int k = std::min(left, c->sweeps_per_launch);
+            rc = launch_fused<T>(c, u0, dev_frames, k, first);
+            first = 0;
+            left -= k;
+        }
+    }
+    if (rc == CLOTHGPU_OK) c->frames++;
+    return rc;
+}
+
+int step_dispatch(clothgpu* c, const clothgpu_frame* frames, int count, bool per_cloth) {
+    return c->precision == CLOTHGPU_F32 ? step_frames<float>(c, frames, count, per_cloth)
+                                        : step_frames<double>(c, frames, count, per_cloth);
+}
+
+template <typename T>
+int init_state(clothgpu* c, int pos_x, int pos_y) {
+    c->cur_pos = c->cur_prev = 0;
+    Planes<T> P = planes<T>(c, 0, 0);
+    init_grid_kernel<T><<<c->sm_count * 8, 256, 0, c->stream>>>(P, c->g, c->ny, c->desc.spacing, pos_x,
+                                                                pos_y, c->desc.pin_rule);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    CU_TRY(cudaMemsetAsync(c->ctr, 0, sizeof(DevCounters), c->stream));
+    c->frames = 0;
+    return CLOTHGPU_OK;
+}
+
+void free_all(clothgpu* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->X[i]);
+        cudaFree(c->Y[i]);
+        cudaFree(c->PX[i]);
+        cudaFree(c->PY[i]);
+        cudaFree(c->FL[i]);
+    }
+    cudaFree(c->ctr);
+    cudaFree(c->census);
+    cudaFree(c->frames_dev);
+    cudaFreeHost(c->frames_host);
+    cudaFree(c->seg_counts);
+    cudaFree(c->seg_out);
+    cudaFree(c->seg_total);
+    if (c->frames_copied) cudaEventDestroy(c->frames_copied);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int check_handle(clothgpu* c) {
+    if (!c) return fail(CLOTHGPU_ERR_INVALID, "null handle");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(CLOTHGPU_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    return CLOTHGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int clothgpu_frame_default(clothgpu_frame* f) {
+    if (!f) return fail(CLOTHGPU_ERR_INVALID, "null frame");
+    memset(f, 0, sizeof *f);
+    // gui/hud.go:86-92 (row i of the slider table feeds enum value i, gui/hud.go:94-97)
+    f->slider[CLOTHGPU_SLIDER_DRAG_FORCE] = 2.0f;
+    f->slider[CLOTHGPU_SLIDER_GRAVITY] = 250.0f;
+    f->slider[CLOTHGPU_SLIDER_STIFFNESS] = 30.0f;
+    f->slider[CLOTHGPU_SLIDER_FRICTION] = 0.98f;
+    f->slider[CLOTHGPU_SLIDER_TEAR_DISTANCE] = 15.0f;
+    f->drag_force_max = 15.0f;
+    f->scroll_y = 50.0f;  // consts.DefaultFocusArea, main.go:84
+    f->win_w = 1280;      // consts.WindowSizeX/Y
+    f->win_h = 820;
+    f->dt = 0.022;        // consts.Delta
+    f->iterations = 1;
+    f->tear_length = 150.0;
+    f->relax_gain = 0.35;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_desc_default(clothgpu_desc* d) {
+    if (!d) return fail(CLOTHGPU_ERR_INVALID, "null desc");
+    memset(d, 0, sizeof *d);
+    d->width = 1024;   // main.go:150-158: clothW = Dp(DefaultWindowWidth)
+    d->height = 211;   // Dp(640 * 0.33) = 211
+    d->spacing = 6;
+    d->pos_x = 128;    // (1280 - 1024) / 2
+    d->pos_y = 164;    // int(820 * 0.2)
+    d->pin_rule = CLOTHGPU_PIN_REFERENCE;
+    d->precision = CLOTHGPU_F64;
+    d->ensemble = 1;
+    d->max_iterations = 1;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
+    if (!desc || !out) return fail(CLOTHGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->spacing <= 0 || desc->width < 0 || desc->height < 0)
+        return fail(CLOTHGPU_ERR_INVALID, "width/height must be >= 0 and spacing > 0");
+    if (desc->precision != CLOTHGPU_F64 && desc->precision != CLOTHGPU_F32)
+        return fail(CLOTHGPU_ERR_INVALID, "unknown precision %d", desc->precision);
+    if (desc->pin_rule < CLOTHGPU_PIN_REFERENCE || desc->pin_rule > CLOTHGPU_PIN_NONE)
+        return fail(CLOTHGPU_ERR_INVALID, "unknown pin rule %d", desc->pin_rule);
+    const int clothX = desc->width / desc->spacing;   // physics/cloth.go:43
+    const int clothY = desc->height / desc->spacing;  // physics/cloth.go:44
+    if (desc->pin_rule == CLOTHGPU_PIN_REFERENCE && clothX / 10 == 0)
+        return fail(CLOTHGPU_ERR_INVALID,
+                    "width/spacing = %d < 10: the reference pin rule divides by zero (physics/cloth.go:72)", clothX);
+    const int ensemble = desc->ensemble < 1 ? 1 : desc->ensemble;
+    const int nx = clothX + 1, ny = clothY + 1;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CLOTHGPU_ERR_NODEVICE, "no CUDA device (%s); clothgpu has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (desc->device < 0 || desc->device >= ndev)
+        return fail(CLOTHGPU_ERR_INVALID, "device %d out of range (have %d)", desc->device, ndev);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, desc->device));
+    if (prop.major != 10)
+        return fail(CLOTHGPU_ERR_NODEVICE, "device %d is sm_%d%d; this library carries sm_100a code only",
+                    desc->device, prop.major, prop.minor);
+    CU_TRY(cudaSetDevice(desc->device));
+
+    clothgpu* c = new (std::nothrow) clothgpu();
+    if (!c) return fail(CLOTHGPU_ERR_NOMEM, "out of host memory");
+    c->desc = *desc;
+    c->desc.ensemble = ensemble;
+    c->ny = ny;
+    c->precision = desc->precision;
+    c->elem = desc->precision == CLOTHGPU_F32 ? 4 : 8;
+    c->device = desc->device;
+    c->sm_count = prop.multiProcessorCount;
+    Geom& g = c->g;
+    g.nx = nx;
+    g.pitch = (nx + 15) / 16 * 16;
+    g.ensemble = ensemble;
+    if (desc->strip_rows > 0) {
+        if (desc->strip_row0 < 0 || desc->strip_row0 + desc->strip_rows > ny || (desc->strip_row0 & 1)) {
+            delete c;
+            return fail(CLOTHGPU_ERR_INVALID, "strip rows [%d,%d) must lie in [0,%d) and start on an even row",
+                        desc->strip_row0, desc->strip_row0 + desc->strip_rows, ny);
+        }
+        const int kmax = desc->max_iterations < 1 ? 1 : desc->max_iterations;
+        c->ghost = 2 * kmax;
+        const int lo = std::max(0, desc->strip_row0 - c->ghost);
+        const int hi = std::min(ny, desc->strip_row0 + desc->strip_rows + c->ghost);
+        g.held_row0 = lo;
+        g.held_rows = hi - lo;
+        g.own_row0 = desc->strip_row0;
+        g.own_rows = desc->strip_rows;
+    } else {
+        g.held_row0 = g.own_row0 = 0;
+        g.held_rows = g.own_rows = ny;
+    }
+    // one spare row keeps the 16-bit flag loads / pair stores of the last row's padding in bounds
+    g.cloth_stride = (long long)(g.held_rows + 1) * g.pitch;
+    c->plane_elems = (size_t)g.cloth_stride * ensemble;
+    if (const char* s = getenv("CLOTHGPU_TILE_ROWS")) c->forced_tile_rows = atoi(s);
+    if (const char* s = getenv("CLOTHGPU_SWEEPS_PER_LAUNCH")) {
+        const int v = atoi(s);
+        if (v >= 1 && v <= kMaxSweepsPerLaunch) c->sweeps_per_launch = v;
+    }
+
+    int rc = CLOTHGPU_OK;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc != CLOTHGPU_OK) return;
+        cudaError_t ee = cudaMalloc(p, bytes);
+        if (ee != cudaSuccess) {
+            rc = fail(ee == cudaErrorMemoryAllocation ? CLOTHGPU_ERR_NOMEM : CLOTHGPU_ERR_CUDA,
+                      "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(ee));
+            cudaGetLastError();
+            return;
+        }
+        ee = cudaMemset(*p, 0, bytes);
+        if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(ee));
+    };
+    for (int i = 0; i < 2; ++i) {
+        alloc(&c->X[i], c->plane_elems * c->elem);
+        alloc(&c->Y[i], c->plane_elems * c->elem);
+        alloc(&c->PX[i], c->plane_elems * c->elem);
+        alloc(&c->PY[i], c->plane_elems * c->elem);
+        alloc((void**)&c->FL[i], c->plane_elems);
+    }
+    alloc((void**)&c->ctr, sizeof(DevCounters));
+    alloc((void**)&c->census, 5 * sizeof(unsigned long long));
+    alloc((void**)&c->seg_total, sizeof(unsigned long long));
+    const size_t fbytes = sizeof(FrameU<double>) * (size_t)ensemble;
+    alloc(&c->frames_dev, fbytes);
+    if (rc == CLOTHGPU_OK) {
+        cudaError_t ee = cudaMallocHost(&c->frames_host, fbytes);
+        if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(ee));
+    }
+    if (rc == CLOTHGPU_OK) {
+        cudaError_t ee = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (ee == cudaSuccess) ee = cudaEventCreate(&c->ev0);
+        if (ee == cudaSuccess) ee = cudaEventCreate(&c->ev1);
+        if (ee == cudaSuccess) ee = cudaEventCreateWithFlags(&c->frames_copied, cudaEventDisableTiming);
+        if (ee == cudaSuccess) ee = cudaEventRecord(c->frames_copied, c->stream);
+        if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_CUDA, "stream/event setup: %s", cudaGetErrorString(ee));
+    }
+    if (rc == CLOTHGPU_OK)
+        rc = c->precision == CLOTHGPU_F32 ? init_state<float>(c, desc->pos_x, desc->pos_y)
+                                          : init_state<double>(c, desc->pos_x, desc->pos_y);
+    if (rc == CLOTHGPU_OK) {
+        cudaError_t ee = cudaStreamSynchronize(c->stream);
+        if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_CUDA, "init kernel: %s", cudaGetErrorString(ee));
+    }
+    if (rc != CLOTHGPU_OK) {
+        std::string keep = g_last_error;
+        free_all(c);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = c;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_reset(clothgpu* c, int32_t pos_x, int32_t pos_y) {
+    if (int rc = check_handle(c)) return rc;
+    c->desc.pos_x = pos_x;
+    c->desc.pos_y = pos_y;
+    return c->precision == CLOTHGPU_F32 ? init_state<float>(c, pos_x, pos_y) : init_state<double>(c, pos_x, pos_y);
+}
+
+void clothgpu_destroy(clothgpu* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_all(c);
+}
+
+int clothgpu_step(clothgpu* c, const clothgpu_frame* frame) {
+    if (int rc = check_handle(c)) return rc;
+    if (!frame) return fail(CLOTHGPU_ERR_INVALID, "null frame");
+    CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    const int rc = step_dispatch(c, frame, 1, false);
+    CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    return rc;
+}
+
+int clothgpu_step_n(clothgpu* c, const clothgpu_frame* frames, int32_t n) {
+    if (int rc = check_handle(c)) return rc;
+    if (!frames || n < 0) return fail(CLOTHGPU_ERR_INVALID, "bad frames/n");
+    CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    int rc = CLOTHGPU_OK;
+    for (int i = 0; i < n && rc == CLOTHGPU_OK; ++i) rc = step_dispatch(c, frames + i, 1, false);
+    CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    return rc;
+}
+
+int clothgpu_step_each(clothgpu* c, const clothgpu_frame* frames, int32_t count) {
+    if (int rc = check_handle(c)) return rc;
+    if (!frames || count != c->g.ensemble)
+        return fail(CLOTHGPU_ERR_INVALID, "step_each needs exactly ensemble=%d frames", c ? c->g.ensemble : 0);
+    CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    const int rc = step_dispatch(c, frames, count, true);
+    CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    return rc;
+}
+
+int clothgpu_sync(clothgpu* c) {
+    if (int rc = check_handle(c)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_get_info(clothgpu* c, clothgpu_info* info) {
+    if (!c || !info) return fail(CLOTHGPU_ERR_INVALID, "null argument");
+    memset(info, 0, sizeof *info);
+    info->nx = c->g.nx;
+    info->ny = c->ny;
+    info->row0 = c->g.own_row0;
+    info->rows = c->g.own_rows;
+    info->ghost = c->ghost;
+    info->pitch = c->g.pitch;
+    info->ensemble = c->g.ensemble;
+    info->precision = c->precision;
+    info->particles = (int64_t)c->g.nx * c->g.own_rows;
+    info->sticks = 2ll * c->g.nx * c->ny - c->g.nx - c->ny;
+    info->device = c->device;
+    info->sm_count = c->sm_count;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_set_schedule(clothgpu* c, int32_t schedule) {
+    if (!c) return fail(CLOTHGPU_ERR_INVALID, "null handle");
+    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_FUSED)
+        return fail(CLOTHGPU_ERR_INVALID, "unknown schedule %d", schedule);
+    c->schedule = schedule;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_read_state(clothgpu* c, int32_t cloth, double* x, double* y, double* px, double* py,
+                        uint8_t* flags) {
+    if (int rc = check_handle(c)) return rc;
+    if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
+    const Geom& g = c->g;
+    const size_t off = (size_t)cloth * g.cloth_stride + (size_t)(g.own_row0 - g.held_row0) * g.pitch;
+    const size_t n = (size_t)g.nx * g.own_rows;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    void* src[4] = {c->X[c->cur_pos], c->Y[c->cur_pos], c->PX[c->cur_prev], c->PY[c->cur_prev]};
+    double* dst[4] = {x, y, px, py};
+    std::vector<float> tmp;
+    for (int k = 0; k < 4; ++k) {
+        if (!dst[k]) continue;
+        if (c->precision == CLOTHGPU_F64) {
+            CU_TRY(cudaMemcpy2D(dst[k], (size_t)g.nx * 8, (const double*)src[k] + off, (size_t)g.pitch * 8,
+                                (size_t)g.nx * 8, g.own_rows, cudaMemcpyDeviceToHost));
+        } else {
+            tmp.resize(n);
+            CU_TRY(cudaMemcpy2D(tmp.data(), (size_t)g.nx * 4, (const float*)src[k] + off, (size_t)g.pitch * 4,
+                                (size_t)g.nx * 4, g.own_rows, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) dst[k][i] = (double)tmp[i];
+        }
+    }
+    if (flags)
+        CU_TRY(cudaMemcpy2D(flags, g.nx, c->FL[c->cur_pos] + off, g.pitch, g.nx, g.own_rows, cudaMemcpyDeviceToHost));
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const double* y, const double* px,
+                         const double* py, const uint8_t* flags) {
+    if (int rc = check_handle(c)) return rc;
+    if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
+    const Geom& g = c->g;
+    const size_t off = (size_t)cloth * g.cloth_stride + (size_t)(g.own_row0 - g.held_row0) * g.pitch;
+    const size_t n = (size_t)g.nx * g.own_rows;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    void* dstp[4] = {c->X[c->cur_pos], c->Y[c->cur_pos], c->PX[c->cur_prev], c->PY[c->cur_prev]};
+    const double* src[4] = {x, y, px, py};
+    std::vector<float> tmp;
+    for (int k = 0; k < 4; ++k) {
+        if (!src[k]) continue;
+        if (c->precision == CLOTHGPU_F64) {
+            CU_TRY(cudaMemcpy2D((double*)dstp[k] + off, (size_t)g.pitch * 8, src[k], (size_t)g.nx * 8,
+                                (size_t)g.nx * 8, g.own_rows, cudaMemcpyHostToDevice));
+        } else {
+            tmp.resize(n);
+            for (size_t i = 0; i < n; ++i) tmp[i] = (float)src[k][i];
+            CU_TRY(cudaMemcpy2D((float*)dstp[k] + off, (size_t)g.pitch * 4, tmp.data(), (size_t)g.nx * 4,
+                                (size_t)g.nx * 4, g.own_rows, cudaMemcpyHostToDevice));
+        }
+    }
+    if (flags) {
+        // keep the invariants Init establishes: no stick past the last column / last row
+        std::vector<uint8_t> fl(flags, flags + n);
+        for (int r = 0; r < g.own_rows; ++r) {
+            fl[(size_t)r * g.nx + g.nx - 1] &= (uint8_t)~CLOTHGPU_FLAG_ALIVE_H;
+            if (g.own_row0 + r == c->ny - 1)
+                for (int q = 0; q < g.nx; ++q) fl[(size_t)r * g.nx + q] &= (uint8_t)~CLOTHGPU_FLAG_ALIVE_V;
+        }
+        CU_TRY(cudaMemcpy2D(c->FL[c->cur_pos] + off, g.pitch, fl.data(), g.nx, g.nx, g.own_rows,
+                            cudaMemcpyHostToDevice));
+    }
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* active, uint32_t* highlighted,
+                        uint32_t* alive_h, uint32_t* alive_v) {
+    if (int rc = check_handle(c)) return rc;
+    if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
+    const Geom& g = c->g;
+    const long long n = (long long)g.nx * g.own_rows;
+    const long long words = (n + 31) / 32;
+    uint32_t* dev = nullptr;
+    CU_TRY(cudaMalloc(&dev, (size_t)words * 5 * sizeof(uint32_t)));
+    const unsigned blocks = (unsigned)((words * 32 + kStreamThreads - 1) / kStreamThreads);
+    if (c->precision == CLOTHGPU_F32)
+        pack_masks_kernel<float><<<blocks, kStreamThreads, 0, c->stream>>>(
+            planes<float>(c, c->cur_pos, c->cur_prev), g, cloth, dev, words);
+    else
+        pack_masks_kernel<double><<<blocks, kStreamThreads, 0, c->stream>>>(
+            planes<double>(c, c->cur_pos, c->cur_prev), g, cloth, dev, words);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    uint32_t* dst[5] = {pin, active, highlighted, alive_h, alive_v};
+    for (int b = 0; b < 5 && e == cudaSuccess; ++b)
+        if (dst[b]) e = cudaMemcpy(dst[b], dev + (size_t)b * words, (size_t)words * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(CLOTHGPU_ERR_CUDA, "read_masks: %s", cudaGetErrorString(e));
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
+                               uint32_t* sticks_idx, size_t cap, size_t* n_out) {
+    if (int rc = check_handle(c)) return rc;
+    if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
+    if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
+    const Geom& g = c->g;
+    const long long n = (long long)g.nx * g.own_rows;
+    const unsigned blocks = (unsigned)((n + kStreamThreads - 1) / kStreamThreads);
+    if (c->seg_counts_cap < blocks) {
+        cudaFree(c->seg_counts);
+        c->seg_counts = nullptr;
+        CU_TRY(cudaMalloc((void**)&c->seg_counts, (size_t)blocks * sizeof(unsigned int)));
+        c->seg_counts_cap = blocks;
+    }
+    const size_t per = sizeof(float4) + sizeof(uint2) + 1;
+    const size_t max_sticks = (size_t)2 * n;
+    if (c->seg_out_cap < max_sticks) {
+        cudaFree(c->seg_out);
+        c->seg_out = nullptr;
+        CU_TRY(cudaMalloc(&c->seg_out, max_sticks * per));
+        c->seg_out_cap = max_sticks;
+    }
+    float4* d_xyxy = (float4*)c->seg_out;
+    uint2* d_idx = (uint2*)(d_xyxy + max_sticks);
+    uint8_t* d_hl = (uint8_t*)(d_idx + max_sticks);
+    if (c->precision == CLOTHGPU_F32) {
+        Planes<float> P = planes<float>(c, c->cur_pos, c->cur_prev);
+        segment_count_kernel<float><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
+        segment_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_counts, (int)blocks, c->seg_total);
+        segment_write_kernel<float><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy,
+                                                                             d_hl, d_idx, max_sticks);
+    } else {
+        Planes<double> P = planes<double>(c, c->cur_pos, c->cur_prev);
+        segment_count_kernel<double><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
+        segment_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_counts, (int)blocks, c->seg_total);
+        segment_write_kernel<double><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy,
+                                                                              d_hl, d_idx, max_sticks);
+    }
+    CU_TRY(cudaGetLastError());
+    c->launches += 3;
+    unsigned long long total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, c->seg_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *n_out = (size_t)total;
+    if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
+    if (total) {
+        if (xyxy) CU_TRY(cudaMemcpy(xyxy, d_xyxy, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost));
+        if (highlighted) CU_TRY(cudaMemcpy(highlighted, d_hl, (size_t)total, cudaMemcpyDeviceToHost));
+        if (sticks_idx) CU_TRY(cudaMemcpy(sticks_idx, d_idx, (size_t)total * sizeof(uint2), cudaMemcpyDeviceToHost));
+    }
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
+    if (int rc = check_handle(c)) return rc;
+    if (!out) return fail(CLOTHGPU_ERR_INVALID, "null out");
+    const Geom& g = c->g;
+    CU_TRY(cudaMemsetAsync(c->census, 0, 5 * sizeof(unsigned long long), c->stream));
+    const long long n = (long long)g.own_rows * g.pitch;
+    dim3 grid((unsigned)((n + kStreamThreads - 1) / kStreamThreads), g.ensemble);
+    if (c->precision == CLOTHGPU_F32)
+        count_kernel<float><<<grid, kStreamThreads, 0, c->stream>>>(planes<float>(c, c->cur_pos, c->cur_prev), g, c->census);
+    else
+        count_kernel<double><<<grid, kStreamThreads, 0, c->stream>>>(planes<double>(c, c->cur_pos, c->cur_prev), g, c->census);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    unsigned long long h5[5];
+    DevCounters hc;
+    CU_TRY(cudaMemcpyAsync(h5, c->census, sizeof h5, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    out->frames = c->frames;
+    out->live_sticks = h5[0];
+    out->alive_sticks = h5[1];
+    out->pinned = h5[2];
+    out->inactive = h5[3];
+    out->highlighted = h5[4];
+    out->torn_last = hc.torn_last;
+    out->relaxations = hc.relaxations;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_halo_region(clothgpu* c, int32_t plane, int32_t which, void** dev_ptr, size_t* bytes) {
+    if (!c || !dev_ptr || !bytes) return fail(CLOTHGPU_ERR_INVALID, "null argument");
+    if (plane < 0 || plane > 4 || which < 0 || which > 3) return fail(CLOTHGPU_ERR_INVALID, "bad plane/which");
+    const Geom& g = c->g;
+    const int above = g.own_row0 - g.held_row0;
+    const int below = (g.held_row0 + g.held_rows) - (g.own_row0 + g.own_rows);
+    int row = 0, rows = 0;  // local (held) row index
+    switch (which) {
+        case 0: row = above; rows = std::min(c->ghost, g.own_rows); break;                      // my top edge
+        case 1: rows = std::min(c->ghost, g.own_rows); row = above + g.own_rows - rows; break;  // my bottom edge
+        case 2: row = 0; rows = above; break;                                                   // top ghost
+        case 3: row = above + g.own_rows; rows = below; break;                                  // bottom ghost
+    }
+    const size_t es = plane == 4 ? 1 : c->elem;
+    char* base = nullptr;
+    switch (plane) {
+        case 0: base = (char*)c->X[c->cur_pos]; break;
+        case 1: base = (char*)c->Y[c->cur_pos]; break;
+        case 2: base = (char*)c->PX[c->cur_prev]; break;
+        case 3: base = (char*)c->PY[c->cur_prev]; break;
+        case 4: base = (char*)c->FL[c->cur_pos]; break;
+    }
+    *dev_ptr = base + (size_t)row * g.pitch * es;
+    *bytes = (size_t)rows * g.pitch * es;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_set_stream(clothgpu* c, void* cuda_stream) {
+    if (int rc = check_handle(c)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_last_step_ms(clothgpu* c, float* ms) {
+    if (int rc = check_handle(c)) return rc;
+    if (!ms) return fail(CLOTHGPU_ERR_INVALID, "null ms");
+    if (!c->timed) return fail(CLOTHGPU_ERR_STATE, "no step has been issued yet");
+    CU_TRY(cudaEventSynchronize(c->ev1));
+    CU_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_launch_count(clothgpu* c, uint64_t* launches) {
+    if (!c || !launches) return fail(CLOTHGPU_ERR_INVALID, "null argument");
+    *launches = c->launches;
+    return CLOTHGPU_OK;
+}
+
+const char* clothgpu_last_error(void) { return g_last_error.c_str(); }
+
+const char* clothgpu_version(void) { return "clothgpu 0.1 (sm_100a)"; }
+
+}  // extern "C"

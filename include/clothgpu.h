@@ -26,6 +26,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CLOTHGPU_API __attribute__((visibility("default")))
+#else
+#define CLOTHGPU_API
+#endif
+
 #define CLOTHGPU_VERSION_MAJOR 0
 #define CLOTHGPU_VERSION_MINOR 1
 
@@ -159,84 +165,85 @@ typedef struct clothgpu_info {
 /* Fill `f` with the reference's defaults: HUD slider defaults (gui/hud.go:86-92), dt = consts.Delta,
  * window consts.WindowSizeX x WindowSizeY, scroll_y = consts.DefaultFocusArea, mouse idle at (0,0),
  * iterations = 1, tear_length = 150, relax_gain = 0.35. */
-int clothgpu_frame_default(clothgpu_frame* f);
+CLOTHGPU_API int clothgpu_frame_default(clothgpu_frame* f);
 
 /* Fill `d` with the reference's default GUI cloth: 1024 x 211 px, spacing 6, origin (128,164),
  * reference pin rule (main.go:149-166). */
-int clothgpu_desc_default(clothgpu_desc* d);
+CLOTHGPU_API int clothgpu_desc_default(clothgpu_desc* d);
 
 /* NewCloth + Init                                                   physics/cloth.go:31-38, 42-81 */
-int clothgpu_create(const clothgpu_desc* desc, clothgpu** out);
+CLOTHGPU_API int clothgpu_create(const clothgpu_desc* desc, clothgpu** out);
 
 /* (*Cloth).Reset(startX, startY, hud): back to the rest grid, all sticks alive, Init pins only.
  *                                                                      physics/cloth.go:142-148   */
-int clothgpu_reset(clothgpu* c, int32_t pos_x, int32_t pos_y);
+CLOTHGPU_API int clothgpu_reset(clothgpu* c, int32_t pos_x, int32_t pos_y);
 
 /* Explicit lifetime (Go side: runtime.SetFinalizer + Close). */
-void clothgpu_destroy(clothgpu* c);
+CLOTHGPU_API void clothgpu_destroy(clothgpu* c);
 
 /* The physics half of (*Cloth).Update: all particle updates, then `iterations` colour-ordered sweeps
  * over all live sticks with tearing.      physics/cloth.go:92-100, particle.go:75-181,
  * constraint.go:25-64.  Asynchronous on the handle's stream. */
-int clothgpu_step(clothgpu* c, const clothgpu_frame* frame);
+CLOTHGPU_API int clothgpu_step(clothgpu* c, const clothgpu_frame* frame);
 
 /* n consecutive frames (headless loop); frames[i] is frame i. */
-int clothgpu_step_n(clothgpu* c, const clothgpu_frame* frames, int32_t n);
+CLOTHGPU_API int clothgpu_step_n(clothgpu* c, const clothgpu_frame* frames, int32_t n);
 
 /* Ensemble handles only: frames[e] drives cloth e (e < ensemble) for one frame. */
-int clothgpu_step_each(clothgpu* c, const clothgpu_frame* frames, int32_t count);
+CLOTHGPU_API int clothgpu_step_each(clothgpu* c, const clothgpu_frame* frames, int32_t count);
 
 /* Block until everything queued on the handle has finished. */
-int clothgpu_sync(clothgpu* c);
+CLOTHGPU_API int clothgpu_sync(clothgpu* c);
 
-int clothgpu_get_info(clothgpu* c, clothgpu_info* info);
-int clothgpu_set_schedule(clothgpu* c, int32_t schedule);
+CLOTHGPU_API int clothgpu_get_info(clothgpu* c, clothgpu_info* info);
+CLOTHGPU_API int clothgpu_set_schedule(clothgpu* c, int32_t schedule);
 
 /* Copy the owned particles of cloth `cloth` to host, row-major, nx per row, no padding.  Any pointer
  * may be NULL.  In F32 handles values are widened to double.  `flags` gets one CLOTHGPU_FLAG_* byte
  * per particle.  This is particle{x,y,px,py,pinX,isActive,highlighted} (physics/particle.go:16-27)
  * plus membership of the two sticks the particle heads in Cloth.constraints. */
-int clothgpu_read_state(clothgpu* c, int32_t cloth, double* x, double* y, double* px, double* py,
+CLOTHGPU_API int clothgpu_read_state(clothgpu* c, int32_t cloth, double* x, double* y, double* px, double* py,
                         uint8_t* flags);
 
 /* Inverse of clothgpu_read_state (restore a snapshot / seed a test state).  NULL planes are kept. */
-int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const double* y,
+CLOTHGPU_API int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const double* y,
                          const double* px, const double* py, const uint8_t* flags);
 
 /* Bit-planes of the flag byte, 1 bit per particle, LSB first, ceil(particles/32) words each; any
  * pointer may be NULL. */
-int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* active,
+CLOTHGPU_API int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* active,
                         uint32_t* highlighted, uint32_t* alive_h, uint32_t* alive_v);
 
 /* The live-stick list the reference's render loops walk (physics/cloth.go:108-114, 126-134):
- * for every stick still in the slice whose endpoints are both active, in row-major order of its
- * head particle (vertical stick first, as Cloth.Init creates them, physics/cloth.go:61-70), the
+ * for every stick still in the slice whose endpoints are both active, in the order Cloth.Init
+ * created them (physics/cloth.go:61-70: by tail particle in row-major order, the vertical stick
+ * from the particle above before the horizontal stick from the particle to the left), the
  * float32 endpoints {x1,y1,x2,y2} and a byte that is 1 when both endpoints are highlighted.
  * `cap` = capacity in sticks; *n = sticks written.  `sticks_idx` (optional) gets {i1,i2} particle
  * indices. */
-int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
+CLOTHGPU_API int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
                                uint32_t* sticks_idx, size_t cap, size_t* n);
 
 /* Counters after the last queued frame (synchronises). */
-int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out);
+CLOTHGPU_API int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out);
 
 /* Strip handles: device pointers/sizes for the halo exchange.
  * plane 0..3 = x,y,px,py, 4 = flags.  `which`: 0 = my top edge rows (to send up), 1 = my bottom
  * edge rows (to send down), 2 = my top ghost rows (to receive), 3 = my bottom ghost rows. */
-int clothgpu_halo_region(clothgpu* c, int32_t plane, int32_t which, void** dev_ptr, size_t* bytes);
+CLOTHGPU_API int clothgpu_halo_region(clothgpu* c, int32_t plane, int32_t which, void** dev_ptr, size_t* bytes);
 
 /* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this handle. */
-int clothgpu_set_stream(clothgpu* c, void* cuda_stream);
+CLOTHGPU_API int clothgpu_set_stream(clothgpu* c, void* cuda_stream);
 
 /* Milliseconds of device time spent in the kernels of the last clothgpu_step / step_n call
  * (CUDA events on the handle's stream); synchronises. */
-int clothgpu_last_step_ms(clothgpu* c, float* ms);
+CLOTHGPU_API int clothgpu_last_step_ms(clothgpu* c, float* ms);
 
 /* Number of kernel launches issued by this handle since create. */
-int clothgpu_launch_count(clothgpu* c, uint64_t* launches);
+CLOTHGPU_API int clothgpu_launch_count(clothgpu* c, uint64_t* launches);
 
-const char* clothgpu_last_error(void);
-const char* clothgpu_version(void);
+CLOTHGPU_API const char* clothgpu_last_error(void);
+CLOTHGPU_API const char* clothgpu_version(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,290 @@
+"""GPU <-> oracle parity through the C ABI (bit-exact in binary64; the reference's own solver cannot run
+here, see oracle/cloth_oracle.h "PARITY UNPINNED")."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import clothgpu
+from clothgpu import _abi
+from clothgpu._abi import (FLAG_ACTIVE, FLAG_ALIVE_H, FLAG_ALIVE_V, FLAG_HIGHLIGHT, FLAG_PIN, MOUSE_DRAGGING,
+                           SCHED_FUSED, SCHED_STREAMING)
+from traces import c0_trace
+
+pytestmark = pytest.mark.gpu
+NAMES = ("x", "y", "px", "py", "flags")
+
+
+def assert_same_state(gpu_state, ora_state, what=""):
+    for n, a, b in zip(NAMES, gpu_state, ora_state):
+        if not np.array_equal(a, b):
+            bad = np.flatnonzero(a != b)
+            raise AssertionError(f"{what}: plane {n} differs at {bad.size} of {a.size} particles, first {bad[:5]}: "
+                                 f"gpu {a[bad[:5]]} oracle {b[bad[:5]]}")
+
+
+def random_state(nx, ny, seed, spacing=6.0, amp=3.0, origin=(128.0, 164.0), kill=0.02, pins=0.01, holes=0.01):
+    """Jittered grid: a mix of stretched and compressed sticks, a few dead sticks, pins and holes."""
+    rng = np.random.default_rng(seed)
+    gx, gy = np.meshgrid(np.arange(nx) * spacing + origin[0], np.arange(ny) * spacing + origin[1])
+    x = (gx + rng.uniform(-amp, amp, gx.shape)).ravel()
+    y = (gy + rng.uniform(-amp, amp, gy.shape)).ravel()
+    px = x + rng.uniform(-0.5, 0.5, x.shape)
+    py = y + rng.uniform(-0.5, 0.5, y.shape)
+    fl = np.full(nx * ny, FLAG_ACTIVE | FLAG_ALIVE_H | FLAG_ALIVE_V, np.uint8)
+    fl2 = fl.reshape(ny, nx)
+    fl2[:, -1] &= ~np.uint8(FLAG_ALIVE_H)
+    fl2[-1, :] &= ~np.uint8(FLAG_ALIVE_V)
+    fl[rng.random(fl.size) < kill] &= ~np.uint8(FLAG_ALIVE_H)
+    fl[rng.random(fl.size) < kill] &= ~np.uint8(FLAG_ALIVE_V)
+    fl[rng.random(fl.size) < pins] |= FLAG_PIN
+    fl[rng.random(fl.size) < holes] &= ~np.uint8(FLAG_ACTIVE)
+    return x, y, px, py, fl
+
+
+def make_pair(oracle, desc, schedule):
+    g = clothgpu.Cloth(desc)
+    g.set_schedule(schedule)
+    o = oracle.OracleCloth(desc, oracle.COLOUR)
+    return g, o
+
+
+@pytest.mark.parametrize("schedule", [SCHED_STREAMING, SCHED_FUSED])
+def test_default_cloth_scripted_trace_bit_exact(oracle, schedule):
+    """BASELINE configs[0]: the reference's default GUI cloth, 1000 frames, drag / hole / tear / ctrl-pin."""
+    desc = _abi.default_desc()
+    g, o = make_pair(oracle, desc, schedule)
+    frames = c0_trace(1000)
+    torn_total = 0
+    for t, f in enumerate(frames):
+        g.step(f)
+        o.step(f)
+        torn_total += o.torn_last
+        if t % 50 == 49 or t in (100, 101, 450, 451, 600, 601, 640, 800, 801):
+            assert_same_state(g.read_state(), o.read_state(), f"frame {t}")
+            c = g.counters()
+            assert c["torn_last"] == o.torn_last, t
+            assert c["relaxations"] == o.relaxations, t
+    c = g.counters()
+    fl = o.read_state()[4]
+    assert torn_total > 50, "the trace is meant to tear sticks"
+    assert c["pinned"] == int(((fl & FLAG_PIN) != 0).sum()) == 12       # 11 Init pins + the ctrl-click
+    assert c["inactive"] == int(((fl & FLAG_ACTIVE) == 0).sum()) > 0
+    assert c["alive_sticks"] == int(((fl & FLAG_ALIVE_H) != 0).sum() + ((fl & FLAG_ALIVE_V) != 0).sum())
+    assert c["frames"] == 1000
+
+
+SHAPES = [(11, 2), (2, 11), (12, 1), (1, 12), (64, 64), (128, 40), (129, 33), (130, 131), (171, 36), (257, 100),
+          (300, 219)]
+
+
+@pytest.mark.parametrize("nx,ny", SHAPES)
+@pytest.mark.parametrize("K", [1, 2, 3, 8, 11])
+def test_random_states_bit_exact(oracle, nx, ny, K):
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=K)
+    st = random_state(nx, ny, seed=nx * 1000 + ny * 7 + K)
+    f = _abi.default_frame(K)
+    f.win_w, f.win_h = 128 + 6 * nx + 50, 164 + 6 * ny + 20        # some particles hit the bounds clamp
+    f.buttons = MOUSE_DRAGGING
+    f.tear_length = 9.5                                           # low threshold: many tears
+    f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 128.0 + 3 * nx, 164.0 + 3 * ny, 120.0 + 3 * nx, 170.0 + 3 * ny
+    results = []
+    for schedule in (SCHED_STREAMING, SCHED_FUSED):
+        g, o = make_pair(oracle, desc, schedule)
+        g.write_state(*st)
+        o.write_state(*st)
+        for t in range(3):
+            g.step(f)
+            o.step(f)
+            assert_same_state(g.read_state(), o.read_state(), f"{nx}x{ny} K={K} sched={schedule} frame {t}")
+            c = g.counters()
+            assert (c["torn_last"], c["relaxations"]) == (o.torn_last, o.relaxations)
+        results.append(g.read_state())
+        g.close()
+    assert_same_state(results[0], results[1], "streaming vs fused")
+
+
+def test_reset_restores_init_state(oracle):
+    desc = _abi.default_desc()
+    g, o = make_pair(oracle, desc, SCHED_FUSED)
+    for f in c0_trace(130):
+        g.step(f)
+    g.reset(100, 90)
+    o.reset(100, 90)
+    assert_same_state(g.read_state(), o.read_state(), "after reset")
+    assert g.counters()["frames"] == 0
+
+
+def test_create_rejects_what_the_reference_panics_on():
+    d = _abi.grid_desc(9, 9, pin_rule=_abi.PIN_REFERENCE)
+    with pytest.raises(clothgpu.ClothGpuError) as e:
+        clothgpu.Cloth(d)
+    assert e.value.code == _abi.ERR_INVALID and "cloth.go:72" in str(e.value)
+
+
+def test_masks_match_flag_bytes():
+    desc = _abi.grid_desc(171, 36, pin_rule=_abi.PIN_REFERENCE)
+    g = clothgpu.Cloth(desc)
+    st = random_state(171, 36, 5)
+    g.write_state(*st)
+    fl = g.read_state()[4]
+    m = g.read_masks()
+    for name, bit in (("pin", FLAG_PIN), ("active", FLAG_ACTIVE), ("highlighted", FLAG_HIGHLIGHT),
+                      ("alive_h", FLAG_ALIVE_H), ("alive_v", FLAG_ALIVE_V)):
+        bits = np.unpackbits(m[name].view(np.uint8), bitorder="little")[: fl.size]
+        assert np.array_equal(bits.astype(bool), (fl & bit) != 0), name
+
+
+def _expected_segments(nx, ny, x, y, fl):
+    """The render loop of physics/cloth.go:108-114 over the creation-ordered slice."""
+    segs, hl = [], []
+    act = (fl & FLAG_ACTIVE) != 0
+    hi = (fl & FLAG_HIGHLIGHT) != 0
+    for r in range(ny):
+        for c in range(nx):
+            p = r * nx + c
+            for q, bit in ((p - nx, FLAG_ALIVE_V), (p - 1, FLAG_ALIVE_H)):
+                if (bit == FLAG_ALIVE_V and r == 0) or (bit == FLAG_ALIVE_H and c == 0):
+                    continue
+                if (fl[q] & bit) and act[q] and act[p]:
+                    segs.append((np.float32(x[q]), np.float32(y[q]), np.float32(x[p]), np.float32(y[p])))
+                    hl.append(hi[q] and hi[p])
+    return np.array(segs, np.float32).reshape(-1, 4), np.array(hl, np.uint8)
+
+
+def test_live_stick_list_matches_reference_render_order(oracle):
+    desc = _abi.default_desc()
+    g, o = make_pair(oracle, desc, SCHED_FUSED)
+    for t, f in enumerate(c0_trace(700)):
+        g.step(f)
+        o.step(f)
+    x, y, px, py, fl = o.read_state()
+    want, want_hl = _expected_segments(g.nx, g.ny, x, y, fl)
+    got, got_hl, idx = g.read_segments(with_indices=True)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(got_hl, want_hl)
+    assert g.counters()["live_sticks"] == len(want)
+    assert np.all(idx[:, 1] > idx[:, 0])
+
+
+def test_ensemble_cloths_are_independent(oracle):
+    nx, ny, E = 128, 128, 5
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, ensemble=E)
+    g = clothgpu.Cloth(desc)
+    one = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW)
+    oracles = [oracle.OracleCloth(one, oracle.COLOUR) for _ in range(E)]
+    for e in range(E):
+        st = random_state(nx, ny, seed=100 + e, pins=0.0)
+        g.write_state(*st, cloth=e)
+        oracles[e].write_state(*st)
+    frames = []
+    for e in range(E):
+        f = _abi.default_frame(8)
+        f.win_w, f.win_h = 2000, 2000
+        f.buttons = MOUSE_DRAGGING if e % 2 else 0
+        f.mouse_x, f.mouse_y = 128.0 + 40 * e, 300.0
+        f.mouse_px, f.mouse_py = f.mouse_x - 3, f.mouse_y + 2
+        f.tear_length = 10.0
+        frames.append(f)
+    for t in range(3):
+        g.step_each(frames)
+        for e in range(E):
+            oracles[e].step(frames[e])
+    for e in range(E):
+        assert_same_state(g.read_state(cloth=e), oracles[e].read_state(), f"cloth {e}")
+    # same frame for everybody
+    g.step(frames[1])
+    for e in range(E):
+        oracles[e].step(frames[1])
+        assert_same_state(g.read_state(cloth=e), oracles[e].read_state(), f"cloth {e} shared frame")
+
+
+def _cudart():
+    import glob
+    import os
+    for pat in ("/usr/local/cuda/lib64/libcudart.so*", "/usr/local/cuda/targets/x86_64-linux/lib/libcudart.so*"):
+        hits = sorted(glob.glob(pat))
+        if hits:
+            return C.CDLL(hits[0])
+    return C.CDLL("libcudart.so")
+
+
+def _exchange_halos_same_device(upper, lower):
+    """Device-to-device halo copy between two strip handles living on one GPU (test stand-in for the
+    NVLink exchange): upper's bottom edge -> lower's top ghost, lower's top edge -> upper's bottom ghost."""
+    rt = _cudart()
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    upper.sync()
+    lower.sync()
+    for plane in range(5):
+        src, n = upper.halo_region(plane, 1)
+        dst, m = lower.halo_region(plane, 2)
+        assert n == m and n > 0
+        assert rt.cudaMemcpy(dst, src, n, 3) == 0
+        src, n = lower.halo_region(plane, 0)
+        dst, m = upper.halo_region(plane, 3)
+        assert n == m and n > 0
+        assert rt.cudaMemcpy(dst, src, n, 3) == 0
+
+
+@pytest.mark.parametrize("schedule", [SCHED_STREAMING, SCHED_FUSED])
+@pytest.mark.parametrize("K", [1, 3])
+def test_two_row_strips_equal_whole_cloth(oracle, schedule, K):
+    """Strip decomposition is exact: 2 strips + ghost-row exchange == whole cloth, bit for bit."""
+    nx, ny, split = 140, 120, 64
+    whole = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K)
+    up = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K, strip_row0=0, strip_rows=split)
+    lo = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K, strip_row0=split, strip_rows=ny - split)
+    g, gu, gl = clothgpu.Cloth(whole), clothgpu.Cloth(up), clothgpu.Cloth(lo)
+    for h in (g, gu, gl):
+        h.set_schedule(schedule)
+    st = random_state(nx, ny, seed=77 + K, pins=0.0)
+    g.write_state(*st)
+    gu.write_state(*[a.reshape(ny, nx)[:split].ravel() for a in st])
+    gl.write_state(*[a.reshape(ny, nx)[split:].ravel() for a in st])
+    _exchange_halos_same_device(gu, gl)
+    f = _abi.default_frame(K)
+    f.win_w, f.win_h = 3000, 3000
+    f.buttons = MOUSE_DRAGGING
+    f.tear_length = 10.0
+    f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 500.0, 164.0 + 6 * split, 495.0, 160.0 + 6 * split
+    for t in range(4):
+        g.step(f)
+        gu.step(f)
+        gl.step(f)
+        _exchange_halos_same_device(gu, gl)
+        full = g.read_state()
+        parts = [np.concatenate([a, b]) for a, b in zip(gu.read_state(), gl.read_state())]
+        assert_same_state(parts, full, f"strips frame {t}")
+    cu, cl, cw = gu.counters(), gl.counters(), g.counters()
+    for k in ("live_sticks", "alive_sticks", "relaxations", "torn_last", "inactive"):
+        assert cu[k] + cl[k] == cw[k], k
+
+
+def test_strip_rejects_too_many_iterations():
+    d = _abi.grid_desc(64, 64, max_iterations=2, strip_row0=0, strip_rows=32)
+    g = clothgpu.Cloth(d)
+    with pytest.raises(clothgpu.ClothGpuError):
+        g.step(_abi.default_frame(3))
+
+
+def test_full_size_1024_fused_equals_streaming_and_oracle(oracle):
+    """BASELINE configs[1] at full size: 1024x1024, K=8, top row pinned.  The oracle (OpenMP) checks the
+    first frames; fused == streaming is the size-independent property for the rest."""
+    desc = _abi.grid_desc(1024, 1024, pin_rule=_abi.PIN_TOP_ROW, max_iterations=8)
+    gf, gs = clothgpu.Cloth(desc), clothgpu.Cloth(desc)
+    gf.set_schedule(SCHED_FUSED)
+    gs.set_schedule(SCHED_STREAMING)
+    o = oracle.OracleCloth(desc, oracle.COLOUR)
+    f = _abi.default_frame(8)
+    f.win_w, f.win_h = 128 + 6 * 1024 + 128, 164 + 6 * 1024 * 4
+    for t in range(6):
+        gf.step(f)
+        gs.step(f)
+        o.step(f, threads=8)
+    assert_same_state(gf.read_state(), o.read_state(), "fused vs oracle")
+    for t in range(40):
+        gf.step(f)
+        gs.step(f)
+    assert_same_state(gf.read_state(), gs.read_state(), "fused vs streaming after 46 frames")
+    assert gf.counters()["relaxations"] == 46 * 8 * (2 * 1024 * 1024 - 2048)
