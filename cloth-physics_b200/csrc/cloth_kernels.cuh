@@ -70,12 +70,20 @@ __global__ void init_grid_kernel(Planes<T> P, Geom g, int ny, int spacing, int p
 
 // Loop over particles (physics/cloth.go:92-94), in place.  One thread per particle of the held rows.
 // `per_cloth` (optional) holds one FrameU per cloth of an ensemble; otherwise every cloth uses u0.
-template <typename T>
+// (PER_CLOTH is a template parameter, not a run-time test: nvcc 12.9 miscompiles the run-time form
+//  `u = u0; if (per_cloth) u = per_cloth[e];` — it keeps reading the first field from the kernel
+//  parameter bank.  tests/test_gpu_parity.py::test_ensemble_cloths_are_independent guards this.)
+template <typename T, bool PER_CLOTH>
+__device__ __forceinline__ FrameU<T> pick_frame(const FrameU<T>& u0, const FrameU<T>* __restrict__ per_cloth, int e) {
+    if (PER_CLOTH) return per_cloth[e];
+    return u0;
+}
+
+template <typename T, bool PER_CLOTH>
 __global__ void __launch_bounds__(kStreamThreads)
     verlet_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth) {
     const int e = blockIdx.y;
-    FrameU<T> u = u0;
-    if (per_cloth) u = per_cloth[e];
+    const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     const long long n = (long long)g.held_rows * g.pitch;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -95,13 +103,12 @@ __global__ void __launch_bounds__(kStreamThreads)
 // One colour pass over the held rows, in place.  COLOUR: 0 H-even, 1 H-odd, 2 V-even, 3 V-odd
 // (parity of the head particle's global column / row).  Each colour is a perfect matching, so the
 // threads of one pass never touch the same particle.
-template <typename T, int COLOUR>
+template <typename T, int COLOUR, bool PER_CLOTH>
 __global__ void __launch_bounds__(kStreamThreads)
     relax_pass_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth,
                       DevCounters* ctr) {
     const int e = blockIdx.y;
-    FrameU<T> u = u0;
-    if (per_cloth) u = per_cloth[e];
+    const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     constexpr bool kVertical = COLOUR >= 2;
     constexpr int kOdd = COLOUR & 1;
     unsigned long long visits = 0, torn = 0;

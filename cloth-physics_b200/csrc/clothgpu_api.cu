@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "cloth_fused.cuh"
@@ -73,6 +74,7 @@ struct clothgpu {
     uint64_t frames = 0;
     uint64_t launches = 0;
     int forced_tile_rows = 0;
+    int fused_variant = 0;  // 0: 512 threads x 2 sticks in flight, 1: 1024 x 1, 2: 512 x 1
     int sweeps_per_launch = kMaxSweepsPerLaunch;
     // scratch for segment export
     unsigned int* seg_counts = nullptr;
@@ -164,13 +166,28 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     // device memory.
     FusedPlan pl = make_plan<T>(c, K, do_verlet);
     const size_t smem = fused_smem_bytes<T>(pl.TH);
-    CU_TRY(cudaFuncSetAttribute(fused_frame_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(227 * 1024)));
     const int nxt = c->cur_pos ^ 1;
     Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
     Planes<T> out = planes<T>(c, nxt, do_verlet ? (c->cur_prev ^ 1) : c->cur_prev);
     dim3 grid(pl.tiles_x, pl.tiles_y, c->g.ensemble);
-    fused_frame_kernel<T><<<grid, kFusedThreads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr);
+    auto go = [&](auto kernel, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, threads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr);
+        return cudaSuccess;
+    };
+    const bool pc = per_cloth != nullptr;
+    switch (c->fused_variant) {
+        case 1:
+            CU_TRY(pc ? go(fused_frame_kernel<T, 1024, 1, true>, 1024) : go(fused_frame_kernel<T, 1024, 1, false>, 1024));
+            break;
+        case 2:
+            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 1, true>, 512) : go(fused_frame_kernel<T, 512, 1, false>, 512));
+            break;
+        default:
+            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 2, true>, 512) : go(fused_frame_kernel<T, 512, 2, false>, 512));
+            break;
+    }
     CU_TRY(cudaGetLastError());
     c->launches++;
     c->cur_pos = nxt;
@@ -185,19 +202,26 @@ int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth
     const FrameU<T>* fr = per_cloth;
     const long long np = (long long)g.held_rows * g.pitch;
     dim3 gp((unsigned)((np + kStreamThreads - 1) / kStreamThreads), g.ensemble);
-    verlet_kernel<T><<<gp, kStreamThreads, 0, c->stream>>>(P, g, u, fr);
-    c->launches++;
     const long long nh = (long long)g.held_rows * std::max(1, g.nx / 2);
     const long long nv = (long long)((g.held_rows + 1) / 2) * g.nx;
     dim3 gh((unsigned)((nh + kStreamThreads - 1) / kStreamThreads), g.ensemble);
     dim3 gv((unsigned)((nv + kStreamThreads - 1) / kStreamThreads), g.ensemble);
-    for (int it = 0; it < u.iterations; ++it) {
-        relax_pass_kernel<T, 0><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-        relax_pass_kernel<T, 1><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-        relax_pass_kernel<T, 2><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-        relax_pass_kernel<T, 3><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-        c->launches += 4;
-    }
+    auto run = [&](auto pcflag) {
+        constexpr bool PC = decltype(pcflag)::value;
+        verlet_kernel<T, PC><<<gp, kStreamThreads, 0, c->stream>>>(P, g, u, fr);
+        c->launches++;
+        for (int it = 0; it < u.iterations; ++it) {
+            relax_pass_kernel<T, 0, PC><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+            relax_pass_kernel<T, 1, PC><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+            relax_pass_kernel<T, 2, PC><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+            relax_pass_kernel<T, 3, PC><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+            c->launches += 4;
+        }
+    };
+    if (fr)
+        run(std::true_type{});
+    else
+        run(std::false_type{});
     CU_TRY(cudaGetLastError());
     return CLOTHGPU_OK;
 }
@@ -404,6 +428,7 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     g.cloth_stride = (long long)(g.held_rows + 1) * g.pitch;
     c->plane_elems = (size_t)g.cloth_stride * ensemble;
     if (const char* s = getenv("CLOTHGPU_TILE_ROWS")) c->forced_tile_rows = atoi(s);
+    if (const char* s = getenv("CLOTHGPU_FUSED_VARIANT")) c->fused_variant = atoi(s);
     if (const char* s = getenv("CLOTHGPU_SWEEPS_PER_LAUNCH")) {
         const int v = atoi(s);
         if (v >= 1 && v <= kMaxSweepsPerLaunch) c->sweeps_per_launch = v;
