@@ -74,7 +74,7 @@ struct clothgpu {
     uint64_t frames = 0;
     uint64_t launches = 0;
     int forced_tile_rows = 0;
-    int fused_variant = 0;  // 0: 512 threads x 2 sticks in flight, 1: 1024 x 1, 2: 512 x 1
+    int fused_variant = 0;  // 0: 512 threads x 1 block (2 sticks) in flight, 1: 512 x 2 blocks, 2: 256 threads x 1, 2 CTAs/SM
     int sweeps_per_launch = kMaxSweepsPerLaunch;
     // scratch for segment export
     unsigned int* seg_counts = nullptr;
@@ -179,13 +179,13 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     const bool pc = per_cloth != nullptr;
     switch (c->fused_variant) {
         case 1:
-            CU_TRY(pc ? go(fused_frame_kernel<T, 1024, 1, true>, 1024) : go(fused_frame_kernel<T, 1024, 1, false>, 1024));
+            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 2, true, 1>, 512) : go(fused_frame_kernel<T, 512, 2, false, 1>, 512));
             break;
         case 2:
-            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 1, true>, 512) : go(fused_frame_kernel<T, 512, 1, false>, 512));
+            CU_TRY(pc ? go(fused_frame_kernel<T, 256, 1, true, 2>, 256) : go(fused_frame_kernel<T, 256, 1, false, 2>, 256));
             break;
         default:
-            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 2, true>, 512) : go(fused_frame_kernel<T, 512, 2, false>, 512));
+            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 1, true, 1>, 512) : go(fused_frame_kernel<T, 512, 1, false, 1>, 512));
             break;
     }
     CU_TRY(cudaGetLastError());
