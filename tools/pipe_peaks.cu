@@ -68,6 +68,29 @@ __global__ void __launch_bounds__(kThreads) smem_kernel(double* out) {
     if (acc.x == 123.456) out[0] = acc.x;
 }
 
+// dependent-issue latency: one warp, one chain, clock64 around it
+__global__ void latency_kernel(double* out, long long* cyc, double a, double b) {
+    double v = threadIdx.x;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) v = fma(v, a, b);
+    long long t1 = clock64();
+    double w = v + 2.0;
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) asm volatile("rsqrt.approx.ftz.f64 %0, %0;" : "+d"(w));
+    long long t2 = clock64();
+    double z = w;
+#pragma unroll 16
+    for (int i = 0; i < 1024; ++i) z = __dadd_rn(z, a);
+    long long t3 = clock64();
+    if (threadIdx.x == 0) {
+        cyc[0] = t1 - t0;
+        cyc[1] = t2 - t1;
+        cyc[2] = t3 - t2;
+    }
+    if (z == 123.456) out[0] = z;
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t a, b;
@@ -103,6 +126,12 @@ int main() {
     const float t_rsq = time_ms([&] { rsq_kernel<<<blocks, kThreads>>>(out, 1.5); });
     cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
     const float t_sm = time_ms([&] { smem_kernel<<<sms, kThreads, 8192 * 16>>>(out); });
+    long long* cyc;
+    cudaMallocManaged(&cyc, 64);
+    latency_kernel<<<1, 32>>>(out, cyc, 1.0000001, 1e-9);
+    cudaDeviceSynchronize();
+    printf("{\"dfma_dep_latency_cycles\": %.2f, \"rsq64h_dep_latency_cycles\": %.2f, \"dadd_dep_latency_cycles\": %.2f}\n",
+           cyc[0] / 1024.0, cyc[1] / 1024.0, cyc[2] / 1024.0);
     const double smem_bytes = (double)sms * kThreads * kIters * 4 * 32.0;
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz_attr\": %d, "
            "\"dfma_thread_inst_per_s\": %.4g, \"dadd_dmul_thread_inst_per_s\": %.4g, \"rsq64h_thread_inst_per_s\": %.4g, "
