@@ -1,0 +1,174 @@
+// Package physics — cgo binding of libclothgpu.so behind the reference's exported surface.
+//
+// SOURCE ONLY: this image has no Go toolchain, so this file is not compiled or tested here; the
+// verifiable boundary is the C ABI (include/clothgpu.h), exercised through the identical entry points by
+// cloth-physics_b200/python/clothgpu (ctypes) and cloth-physics_b200/host/physics.hpp (C++).
+//
+// Drop-in recipe (INTEGRATION.md): in a checkout of esimov/cloth-physics delete physics/particle.go and
+// physics/constraint.go, replace physics/cloth.go by this file, keep physics/mouse.go unchanged and add
+// mouse_frame.go next to it.  main.go keeps calling
+//
+//	cloth := physics.NewCloth(w, h, spacing, col)   // physics/cloth.go:31  (main.go:158)
+//	cloth.Init(startX, startY, hud)                  // physics/cloth.go:42  (main.go:166,217)
+//	cloth.Update(gtx, mouse, hud, delta)             // physics/cloth.go:85  (main.go:310)
+//	cloth.Reset(startX, startY, hud)                 // physics/cloth.go:142 (main.go:193)
+//
+// and reads/writes cloth.Width / cloth.Height exactly as before.
+package physics
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../csrc -lclothgpu -Wl,-rpath,${SRCDIR}/../../../csrc
+#include <stdlib.h>
+#include "clothgpu.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"image/color"
+	"math"
+	"runtime"
+	"unsafe"
+
+	"gioui.org/f32"
+	"gioui.org/layout"
+	"gioui.org/op/clip"
+	"gioui.org/op/paint"
+
+	"github.com/esimov/cloth-physics/gui"
+)
+
+const strokeWidth = 0.6
+
+// Cloth keeps the exported fields of the reference type (physics/cloth.go:18-27); particles and sticks
+// live in HBM behind the handle.
+type Cloth struct {
+	Width  int
+	Height int
+
+	spacing int
+	tint    color.NRGBA
+	gpu     *C.clothgpu
+	// host staging for the render export, reused across frames
+	segs []float32
+	hl   []uint8
+}
+
+// NewCloth mirrors physics/cloth.go:31-38.  No device work happens until Init.
+func NewCloth(width, height, spacing int, col color.NRGBA) *Cloth {
+	return &Cloth{Width: width, Height: height, spacing: spacing, tint: col}
+}
+
+// Init mirrors physics/cloth.go:42-81: idempotent once initialised.  The reference panics with an
+// integer divide by zero when Width/spacing < 10 (cloth.go:72); clothgpu_create reports the same
+// condition as CLOTHGPU_ERR_INVALID and we turn it back into a panic.
+func (c *Cloth) Init(posX, posY int, hud *gui.Hud) {
+	if c.gpu != nil {
+		return
+	}
+	var d C.clothgpu_desc
+	C.clothgpu_desc_default(&d)
+	d.width, d.height, d.spacing = C.int32_t(c.Width), C.int32_t(c.Height), C.int32_t(c.spacing)
+	d.pos_x, d.pos_y = C.int32_t(posX), C.int32_t(posY)
+	d.pin_rule = C.CLOTHGPU_PIN_REFERENCE
+	d.precision = C.CLOTHGPU_F64
+	if rc := C.clothgpu_create(&d, &c.gpu); rc != C.CLOTHGPU_OK {
+		panic(fmt.Sprintf("clothgpu_create: %s", C.GoString(C.clothgpu_last_error())))
+	}
+	runtime.SetFinalizer(c, (*Cloth).Close)
+}
+
+// Reset mirrors physics/cloth.go:142-148.
+func (c *Cloth) Reset(startX, startY int, hud *gui.Hud) {
+	if c.gpu == nil {
+		c.Init(startX, startY, hud)
+		return
+	}
+	// Width/Height may have been changed by main.go:190-191; a different grid needs a new handle.
+	var info C.clothgpu_info
+	C.clothgpu_get_info(c.gpu, &info)
+	if int(info.nx) != c.Width/c.spacing+1 || int(info.ny) != c.Height/c.spacing+1 {
+		c.Close()
+		c.Init(startX, startY, hud)
+		return
+	}
+	c.check(C.clothgpu_reset(c.gpu, C.int32_t(startX), C.int32_t(startY)))
+}
+
+// Close releases the device memory (the reference relies on the GC; there is no counterpart).
+func (c *Cloth) Close() {
+	if c.gpu != nil {
+		C.clothgpu_destroy(c.gpu)
+		c.gpu = nil
+	}
+}
+
+// Update mirrors physics/cloth.go:85-138: the physics half runs on the GPU, the render half walks the
+// compacted live-stick list the device exports (same order and same float32 endpoints as the two
+// loops of cloth.go:108-114 and 126-134).
+func (c *Cloth) Update(gtx layout.Context, mouse *Mouse, hud *gui.Hud, dt float64) {
+	var f C.clothgpu_frame
+	C.clothgpu_frame_default(&f)
+	// particle.go:78-83: the five sliders are read as float32 and widened at the point of use
+	f.slider[C.CLOTHGPU_SLIDER_DRAG_FORCE] = C.float(hud.Sliders[gui.HudSliderDragForce].Widget.Value)
+	f.slider[C.CLOTHGPU_SLIDER_GRAVITY] = C.float(hud.Sliders[gui.HudSliderGravityForce].Widget.Value)
+	f.slider[C.CLOTHGPU_SLIDER_STIFFNESS] = C.float(hud.Sliders[gui.HudSliderStiffness].Widget.Value)
+	f.slider[C.CLOTHGPU_SLIDER_FRICTION] = C.float(hud.Sliders[gui.HudSliderFriction].Widget.Value)
+	f.slider[C.CLOTHGPU_SLIDER_TEAR_DISTANCE] = C.float(hud.Sliders[gui.HudSliderTearDistance].Widget.Value)
+	f.drag_force_max = C.float(hud.Sliders[gui.HudSliderDragForce].Max) // particle.go:97
+	mouse.fillFrame(unsafe.Pointer(&f))                                  // mouse_frame.go
+	f.win_w = C.int32_t(gtx.Constraints.Max.X)                          // particle.go:102
+	f.win_h = C.int32_t(gtx.Constraints.Max.Y)
+	f.win_off_x, f.win_off_y = C.double(hud.WinOffsetX), C.double(hud.WinOffsetY) // particle.go:89-90
+	f.dt = C.double(dt)
+	f.iterations = 1 // the reference relaxes once per frame (cloth.go:96-100)
+	c.check(C.clothgpu_step(c.gpu, &f))
+
+	// render half, cloth.go:102-138
+	var info C.clothgpu_info
+	C.clothgpu_get_info(c.gpu, &info)
+	capSticks := int(info.sticks)
+	if cap(c.segs) < 4*capSticks {
+		c.segs = make([]float32, 4*capSticks)
+		c.hl = make([]uint8, capSticks)
+	}
+	var n C.size_t
+	c.check(C.clothgpu_read_segments_f32(c.gpu, 0, (*C.float)(unsafe.Pointer(&c.segs[0])),
+		(*C.uint8_t)(unsafe.Pointer(&c.hl[0])), nil, C.size_t(capSticks), &n))
+
+	var path clip.Path
+	path.Begin(gtx.Ops)
+	for i := 0; i < int(n); i++ {
+		quad(&path, f32.Pt(c.segs[4*i], c.segs[4*i+1]), f32.Pt(c.segs[4*i+2], c.segs[4*i+3]), strokeWidth)
+	}
+	paint.FillShape(gtx.Ops, c.tint, clip.Outline{Path: path.End()}.Op())
+	path.Begin(gtx.Ops)
+	for i := 0; i < int(n); i++ {
+		if c.hl[i] != 0 {
+			quad(&path, f32.Pt(c.segs[4*i], c.segs[4*i+1]), f32.Pt(c.segs[4*i+2], c.segs[4*i+3]), strokeWidth)
+		}
+	}
+	paint.FillShape(gtx.Ops, color.NRGBA{R: c.tint.R, A: c.tint.A}, clip.Outline{Path: path.End()}.Op())
+}
+
+// quad emits the stroke outline of one stick (cloth.go:150-168 does the same with a unit normal).
+func quad(p *clip.Path, a, b f32.Point, w float32) {
+	d := b.Sub(a)
+	l := float32(math.Hypot(float64(d.X), float64(d.Y)))
+	if l == 0 {
+		return
+	}
+	n := f32.Pt(-d.Y*w/l, d.X*w/l)
+	p.MoveTo(a.Add(n))
+	p.LineTo(b.Add(n))
+	p.LineTo(b.Sub(n))
+	p.LineTo(a.Sub(n))
+	p.Close()
+}
+
+func (c *Cloth) check(rc C.int) {
+	if rc != C.CLOTHGPU_OK {
+		panic(fmt.Sprintf("clothgpu: %s", C.GoString(C.clothgpu_last_error())))
+	}
+}
