@@ -2,6 +2,7 @@
 // the sm_100a kernels, read-back.  No CPU compute path exists here: every physics result comes from
 // the kernels in cloth_kernels.cuh / cloth_fused.cuh.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +40,7 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                 \
     } while (0)
 
+constexpr double kMaxMagnitude = 1e30;  // |frame values| and |coordinates| accepted from the host
 constexpr int kMaxSweepsPerLaunch = 8;  // halo 16; larger K is split into several launches
 
 }  // namespace
@@ -176,16 +178,26 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
         kernel<<<grid, threads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr);
         return cudaSuccess;
     };
+    // PER_CLOTH: every cloth has its own frame block (buttons differ), so the tear test stays in.  Otherwise the
+    // DRAG=false instantiation drops it for frames without a drag (the common case).
     const bool pc = per_cloth != nullptr;
+    const bool drag = pc || (u.buttons & CLOTHGPU_MOUSE_DRAGGING);
+    auto pick = [&](auto nt, auto blk, auto ctas) -> cudaError_t {
+        constexpr int NT = decltype(nt)::value, BLK = decltype(blk)::value, CT = decltype(ctas)::value;
+        if (pc) return go(fused_frame_kernel<T, NT, BLK, true, true, CT>, NT);
+        return drag ? go(fused_frame_kernel<T, NT, BLK, false, true, CT>, NT)
+                    : go(fused_frame_kernel<T, NT, BLK, false, false, CT>, NT);
+    };
+    using std::integral_constant;
     switch (c->fused_variant) {
         case 1:
-            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 2, true, 1>, 512) : go(fused_frame_kernel<T, 512, 2, false, 1>, 512));
+            CU_TRY(pick(integral_constant<int, 512>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{}));
             break;
         case 2:
-            CU_TRY(pc ? go(fused_frame_kernel<T, 256, 1, true, 2>, 256) : go(fused_frame_kernel<T, 256, 1, false, 2>, 256));
+            CU_TRY(pick(integral_constant<int, 256>{}, integral_constant<int, 1>{}, integral_constant<int, 2>{}));
             break;
         default:
-            CU_TRY(pc ? go(fused_frame_kernel<T, 512, 1, true, 1>, 512) : go(fused_frame_kernel<T, 512, 1, false, 1>, 512));
+            CU_TRY(pick(integral_constant<int, 512>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{}));
             break;
     }
     CU_TRY(cudaGetLastError());
@@ -234,9 +246,17 @@ namespace {
 
 template <typename T>
 int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_cloth) {
-    // validate first
+    // validate first.  Every frame value must be finite and of sane magnitude: with finite inputs the update can
+    // neither produce a non-finite coordinate nor leave the range the shared-seed sqrt/div expansion is exact on
+    // (cloth_fused.cuh), so the kernels carry no per-stick range test.  (The Go code would propagate NaN instead.)
     for (int i = 0; i < count; ++i) {
         const clothgpu_frame& f = frames[i];
+        const double vals[] = {f.slider[0], f.slider[1], f.slider[2], f.slider[3], f.slider[4], f.drag_force_max,
+                               f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py, f.mouse_force, f.scroll_y,
+                               f.win_off_x, f.win_off_y, f.dt, f.tear_length, f.relax_gain};
+        for (double v : vals)
+            if (!(std::fabs(v) <= kMaxMagnitude))
+                return fail(CLOTHGPU_ERR_INVALID, "frame %d holds a non-finite or absurd value (%g)", i, v);
         const int K = f.iterations < 1 ? 1 : f.iterations;
         if (c->desc.strip_rows > 0 && 2 * K > c->ghost)
             return fail(CLOTHGPU_ERR_INVALID, "iterations=%d needs %d ghost rows, handle has %d (raise desc.max_iterations)",
@@ -604,15 +624,25 @@ int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const doub
     CU_TRY(cudaStreamSynchronize(c->stream));
     void* dstp[4] = {c->X[c->cur_pos], c->Y[c->cur_pos], c->PX[c->cur_prev], c->PY[c->cur_prev]};
     const double* src[4] = {x, y, px, py};
+    // coordinates must be finite (see step_frames); -0.0 is stored as +0.0 — the update never produces -0.0 from
+    // other inputs, and the kernels rely on p + 0 == p for every stored value
+    for (int k = 0; k < 4; ++k)
+        if (src[k])
+            for (size_t i = 0; i < n; ++i)
+                if (!(std::fabs(src[k][i]) <= kMaxMagnitude))
+                    return fail(CLOTHGPU_ERR_INVALID, "write_state: plane %d element %zu is not finite / too large (%g)", k, i, src[k][i]);
     std::vector<float> tmp;
+    std::vector<double> tmpd;
     for (int k = 0; k < 4; ++k) {
         if (!src[k]) continue;
         if (c->precision == CLOTHGPU_F64) {
-            CU_TRY(cudaMemcpy2D((double*)dstp[k] + off, (size_t)g.pitch * 8, src[k], (size_t)g.nx * 8,
+            tmpd.resize(n);
+            for (size_t i = 0; i < n; ++i) tmpd[i] = src[k][i] + 0.0;  // -0.0 + 0.0 == +0.0
+            CU_TRY(cudaMemcpy2D((double*)dstp[k] + off, (size_t)g.pitch * 8, tmpd.data(), (size_t)g.nx * 8,
                                 (size_t)g.nx * 8, g.own_rows, cudaMemcpyHostToDevice));
         } else {
             tmp.resize(n);
-            for (size_t i = 0; i < n; ++i) tmp[i] = (float)src[k][i];
+            for (size_t i = 0; i < n; ++i) tmp[i] = (float)src[k][i] + 0.0f;
             CU_TRY(cudaMemcpy2D((float*)dstp[k] + off, (size_t)g.pitch * 4, tmp.data(), (size_t)g.nx * 4,
                                 (size_t)g.nx * 4, g.own_rows, cudaMemcpyHostToDevice));
         }
