@@ -76,7 +76,7 @@ struct clothgpu {
     uint64_t frames = 0;
     uint64_t launches = 0;
     int forced_tile_rows = 0;
-    int fused_variant = 0;  // 0: 512 threads x 1 block (2 sticks) in flight, 1: 512 x 2 blocks, 2: 256 threads x 1, 2 CTAs/SM
+    int fused_variant = -1;  // -1: chosen per launch (choose_variant); >= 0: forced, see launch_fused
     int sweeps_per_launch = kMaxSweepsPerLaunch;
     // scratch for segment export
     unsigned int* seg_counts = nullptr;
@@ -101,8 +101,20 @@ Planes<T> planes(clothgpu* c, int pos, int prev) {
 
 // Tile-row choice for the fused kernel: the largest tile that fits shared memory minimises halo
 // overhead, but the number of tiles should fill whole waves of SMs; cost ~ waves * tile rows.
+// CTAs the variant is built to co-host per SM (its __launch_bounds__ minimum)
+int variant_ctas(int variant) { return variant == 2 ? 2 : variant == 5 ? 3 : 1; }
+
+// Which instantiation runs a launch of K sweeps.  Few sweeps: the launch is bound by HBM latency/bandwidth, so small
+// tiles with 3 CTAs per SM overlap one tile's load/store with another's arithmetic.  Many sweeps: the halo (2K per
+// side) must be amortised over the largest tile shared memory holds, one CTA per SM with as many warps as the
+// register file allows.  CLOTHGPU_FUSED_VARIANT overrides (tuning/tests).
+int choose_variant(const clothgpu* c, int K) {
+    if (c->fused_variant >= 0) return c->fused_variant;
+    return K <= 2 ? 5 : 4;
+}
+
 template <typename T>
-FusedPlan make_plan(const clothgpu* c, int K, int do_verlet) {
+FusedPlan make_plan(const clothgpu* c, int K, int do_verlet, int variant) {
     const Geom& g = c->g;
     FusedPlan pl{};
     pl.K = K;
@@ -124,10 +136,16 @@ FusedPlan make_plan(const clothgpu* c, int K, int do_verlet) {
     const int below = (g.held_row0 + g.held_rows) - (g.own_row0 + g.own_rows);
     pl.top_margin = std::min(h, above);
     const int bottom_margin = std::min(h, below);
-    const size_t smem_max = 227 * 1024;
+    // shared memory per CTA when `ctas` CTAs are to co-reside on an SM (228 KB per SM, 1 KB reserved per CTA)
+    const int ctas = variant_ctas(variant);
+    const size_t smem_max = ctas == 1 ? 227 * 1024 : (size_t)(228 * 1024) / ctas - 1024;
     int th_max = 2;
     while (fused_smem_bytes<T>(th_max + 2) <= smem_max) th_max += 2;
     const int th_min = 2 * h + 2;
+    if (th_max < th_min) {  // this variant's tiles cannot hold the halo of K sweeps
+        pl.TH = 0;
+        return pl;
+    }
     auto tiles_y_for = [&](int TH, int* first_h) {
         if (pl.top_margin + g.own_rows + bottom_margin <= TH) {
             *first_h = g.own_rows;
@@ -146,7 +164,8 @@ FusedPlan make_plan(const clothgpu* c, int K, int do_verlet) {
             int fh;
             const int ty = tiles_y_for(TH, &fh);
             const long long tiles = (long long)ty * pl.tiles_x * g.ensemble;
-            const long long waves = (tiles + c->sm_count - 1) / c->sm_count;
+            const long long slots = (long long)c->sm_count * ctas;
+            const long long waves = (tiles + slots - 1) / slots;
             // a tile costs ~ its rows (+ a little fixed overhead); small tiles may co-reside 2 per SM
             const double cost = (double)waves * (TH + 6);
             if (cost < best_cost - 1e-9) {
@@ -166,7 +185,12 @@ template <typename T>
 int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, int K, int do_verlet) {
     // The frame block travels by value in the kernel parameters; per-cloth blocks (ensembles) through
     // device memory.
-    FusedPlan pl = make_plan<T>(c, K, do_verlet);
+    int variant = choose_variant(c, K);
+    FusedPlan pl = make_plan<T>(c, K, do_verlet, variant);
+    if (pl.TH == 0) {
+        variant = 4;
+        pl = make_plan<T>(c, K, do_verlet, variant);
+    }
     const size_t smem = fused_smem_bytes<T>(pl.TH);
     const int nxt = c->cur_pos ^ 1;
     Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
@@ -189,12 +213,21 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
                     : go(fused_frame_kernel<T, NT, BLK, false, false, CT>, NT);
     };
     using std::integral_constant;
-    switch (c->fused_variant) {
+    switch (variant) {
         case 1:
             CU_TRY(pick(integral_constant<int, 512>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{}));
             break;
         case 2:
             CU_TRY(pick(integral_constant<int, 256>{}, integral_constant<int, 1>{}, integral_constant<int, 2>{}));
+            break;
+        case 5:
+            CU_TRY(pick(integral_constant<int, 256>{}, integral_constant<int, 1>{}, integral_constant<int, 3>{}));
+            break;
+        case 3:
+            CU_TRY(pick(integral_constant<int, 640>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{}));
+            break;
+        case 4:
+            CU_TRY(pick(integral_constant<int, 768>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{}));
             break;
         default:
             CU_TRY(pick(integral_constant<int, 512>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{}));
