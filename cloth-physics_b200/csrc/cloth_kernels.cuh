@@ -354,4 +354,53 @@ __global__ void __launch_bounds__(kStreamThreads)
     }
 }
 
+// ---- row strips over several GPUs: stream-ordered handshake and the explicit edge-row push -----------------------
+// Every strip owns two 32-bit epoch slots in its own memory: slot 0 is written by its upper neighbour, slot 1 by
+// its lower neighbour.  Operation k of a strip (a fused launch, or a push) may start once both neighbours have
+// finished their operation k-1: their stores into my ghost rows have landed, and they no longer read the buffer
+// I am about to write.  Afterwards the strip publishes k in both neighbours' slots.
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void strip_wait_kernel(const unsigned int* my_slots, int wait_up, int wait_dn, unsigned int need) {
+    // epochs only grow; the signed difference tolerates wrap-around
+    if (wait_up)
+        while ((int)(ld_acquire_sys(my_slots + 0) - need) < 0) __nanosleep(64);
+    if (wait_dn)
+        while ((int)(ld_acquire_sys(my_slots + 1) - need) < 0) __nanosleep(64);
+}
+
+__global__ void strip_signal_kernel(unsigned int* up_slot, unsigned int* dn_slot, unsigned int epoch) {
+    __threadfence_system();  // everything this stream wrote before (incl. peer stores of the frame kernel)
+    if (up_slot) st_release_sys(up_slot, epoch);
+    if (dn_slot) st_release_sys(dn_slot, epoch);
+}
+
+// Copy my owned rows that a neighbour keeps as ghosts into its memory (all five planes).  Used after the state was
+// written from the host (clothgpu_write_state) — per-frame traffic goes through the fused kernel itself.
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads)
+    strip_push_kernel(Planes<T> mine, Geom g, PeerOut<T> peer) {
+    const int e = blockIdx.y;
+    const int rows = peer.row_hi - peer.row_lo;
+    const long long n = (long long)rows * g.pitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / g.pitch), cx = (int)(i - (long long)r * g.pitch);
+        const int gy = peer.row_lo + r;
+        const long long at = (long long)e * g.cloth_stride + (long long)(gy - g.held_row0) * g.pitch + cx;
+        const long long pat = (long long)e * peer.cloth_stride + (long long)(gy - peer.held_row0) * g.pitch + cx;
+        peer.x[pat] = mine.x[at];
+        peer.y[pat] = mine.y[at];
+        peer.px[pat] = mine.px[at];
+        peer.py[pat] = mine.py[at];
+        peer.fl[pat] = mine.fl[at];
+    }
+}
+
 }  // namespace clothgpu_impl

@@ -25,6 +25,22 @@ struct Planes {
     uint8_t* fl;
 };
 
+// Row-strip decomposition over several GPUs: where a neighbouring strip keeps copies ("ghost rows") of some of
+// my owned rows.  The planes are the neighbour's buffers this launch must fill (its `out` side), mapped into
+// this process over NVLink (cudaIpcOpenMemHandle) or plain pointers when the neighbour lives in this process.
+// rows [row_lo, row_hi) are GLOBAL rows; empty when there is no neighbour on that side.
+template <typename T>
+struct PeerOut {
+    T* x;
+    T* y;
+    T* px;
+    T* py;
+    uint8_t* fl;
+    long long cloth_stride;  // the neighbour's elements between consecutive cloths
+    int held_row0;           // global index of the neighbour's first held row
+    int row_lo, row_hi;
+};
+
 // Geometry of what one handle holds.  "Held" rows = owned rows plus ghost rows (strips only).
 struct Geom {
     int nx;            // particles per row of the cloth

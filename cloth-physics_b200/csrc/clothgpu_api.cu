@@ -12,6 +12,8 @@
 #include <type_traits>
 #include <vector>
 
+#include <unistd.h>
+
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
 #include "frame_fold.h"
@@ -78,6 +80,24 @@ struct clothgpu {
     int forced_tile_rows = 0;
     int fused_variant = -1;  // -1: chosen per launch (choose_variant); >= 0: forced, see launch_fused
     int sweeps_per_launch = kMaxSweepsPerLaunch;
+    // All state planes and the strip epoch slots live in ONE device allocation, so a neighbouring strip (another
+    // process, another GPU) maps everything with a single cudaIpcMemHandle.
+    void* slab = nullptr;
+    size_t slab_bytes = 0;
+    size_t off_plane[10] = {0};  // X0 X1 Y0 Y1 PX0 PX1 PY0 PY1 FL0 FL1
+    size_t off_slots = 0;
+    unsigned int* slots = nullptr;  // [0] written by my upper neighbour, [1] by my lower neighbour
+    struct Link {
+        bool on = false;
+        bool ipc = false;      // base came from cudaIpcOpenMemHandle (must be closed)
+        char* base = nullptr;  // the neighbour's slab, mapped here
+        size_t off_plane[10] = {0};
+        size_t off_slots = 0;
+        long long cloth_stride = 0;
+        int held_row0 = 0, held_rows = 0;
+        int row_lo = 0, row_hi = 0;  // my owned rows the neighbour keeps as ghosts
+    } link[2];                       // 0 = upper neighbour, 1 = lower neighbour
+    unsigned int epoch = 0;          // operations (fused launches, pushes) done since attach
     // scratch for segment export
     unsigned int* seg_counts = nullptr;
     size_t seg_counts_cap = 0;
@@ -181,6 +201,47 @@ FusedPlan make_plan(const clothgpu* c, int K, int do_verlet, int variant) {
     return pl;
 }
 
+// The neighbour's buffers with the given indices, as the target of this operation's edge-row stores.
+template <typename T>
+PeerOut<T> peer_out(const clothgpu* c, int side, int pos, int prev) {
+    PeerOut<T> p{};
+    const clothgpu::Link& l = c->link[side];
+    if (!l.on) return p;  // row_lo == row_hi == 0: no row matches
+    p.x = (T*)(l.base + l.off_plane[0 + pos]);
+    p.y = (T*)(l.base + l.off_plane[2 + pos]);
+    p.px = (T*)(l.base + l.off_plane[4 + prev]);
+    p.py = (T*)(l.base + l.off_plane[6 + prev]);
+    p.fl = (uint8_t*)(l.base + l.off_plane[8 + pos]);
+    p.cloth_stride = l.cloth_stride;
+    p.held_row0 = l.held_row0;
+    p.row_lo = l.row_lo;
+    p.row_hi = l.row_hi;
+    return p;
+}
+
+bool attached(const clothgpu* c) { return c->link[0].on || c->link[1].on; }
+
+// Operation k may start once both neighbours finished operation k-1 (cloth_kernels.cuh).
+int strip_begin_op(clothgpu* c) {
+    if (!attached(c)) return CLOTHGPU_OK;
+    strip_wait_kernel<<<1, 1, 0, c->stream>>>(c->slots, c->link[0].on, c->link[1].on, c->epoch);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CLOTHGPU_OK;
+}
+
+int strip_end_op(clothgpu* c) {
+    if (!attached(c)) return CLOTHGPU_OK;
+    c->epoch++;
+    // I am the LOWER neighbour of my upper neighbour: its slot 1; and the UPPER neighbour of my lower one: its slot 0
+    unsigned int* up = c->link[0].on ? (unsigned int*)(c->link[0].base + c->link[0].off_slots) + 1 : nullptr;
+    unsigned int* dn = c->link[1].on ? (unsigned int*)(c->link[1].base + c->link[1].off_slots) + 0 : nullptr;
+    strip_signal_kernel<<<1, 1, 0, c->stream>>>(up, dn, c->epoch);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return CLOTHGPU_OK;
+}
+
 template <typename T>
 int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, int K, int do_verlet) {
     // The frame block travels by value in the kernel parameters; per-cloth blocks (ensembles) through
@@ -194,12 +255,16 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     const size_t smem = fused_smem_bytes<T>(pl.TH);
     const int nxt = c->cur_pos ^ 1;
     Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
-    Planes<T> out = planes<T>(c, nxt, do_verlet ? (c->cur_prev ^ 1) : c->cur_prev);
+    const int nprev = do_verlet ? (c->cur_prev ^ 1) : c->cur_prev;
+    Planes<T> out = planes<T>(c, nxt, nprev);
+    // strips: the neighbours run the same operation sequence, so their buffer indices equal mine
+    const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
+    if (int rc = strip_begin_op(c)) return rc;
     dim3 grid(pl.tiles_x, pl.tiles_y, c->g.ensemble);
     auto go = [&](auto kernel, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return e;
-        kernel<<<grid, threads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr);
+        kernel<<<grid, threads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr, pup, pdn);
         return cudaSuccess;
     };
     // PER_CLOTH: every cloth has its own frame block (buttons differ), so the tear test stays in.  Otherwise the
@@ -237,7 +302,7 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     c->launches++;
     c->cur_pos = nxt;
     if (do_verlet) c->cur_prev ^= 1;
-    return CLOTHGPU_OK;
+    return strip_end_op(c);
 }
 
 template <typename T>
@@ -291,9 +356,11 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
             if (!(std::fabs(v) <= kMaxMagnitude))
                 return fail(CLOTHGPU_ERR_INVALID, "frame %d holds a non-finite or absurd value (%g)", i, v);
         const int K = f.iterations < 1 ? 1 : f.iterations;
-        if (c->desc.strip_rows > 0 && 2 * K > c->ghost)
+        // attached strips refresh their ghost rows after every launch, detached ones once per frame (by the caller)
+        const int depth = 2 * (attached(c) ? std::min(K, c->sweeps_per_launch) : K);
+        if (c->desc.strip_rows > 0 && depth > c->ghost)
             return fail(CLOTHGPU_ERR_INVALID, "iterations=%d needs %d ghost rows, handle has %d (raise desc.max_iterations)",
-                        K, 2 * K, c->ghost);
+                        K, depth, c->ghost);
         if (per_cloth && K != (frames[0].iterations < 1 ? 1 : frames[0].iterations))
             return fail(CLOTHGPU_ERR_INVALID, "per-cloth frames must share `iterations`");
     }
@@ -310,6 +377,10 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     }
     CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, sizeof(unsigned long long), c->stream));
     int sched = c->schedule == CLOTHGPU_SCHED_AUTO ? CLOTHGPU_SCHED_FUSED : c->schedule;
+    if (attached(c) && sched != CLOTHGPU_SCHED_FUSED)
+        return fail(CLOTHGPU_ERR_STATE, "attached strips exchange their edge rows inside the fused kernel; the streaming schedule is for detached handles");
+    if (c->desc.strip_rows > 0 && !attached(c) && sched == CLOTHGPU_SCHED_FUSED && u0.iterations > c->sweeps_per_launch)
+        return fail(CLOTHGPU_ERR_STATE, "a detached strip cannot split %d sweeps over several launches (ghost rows would go stale between launches); attach the neighbours or use <= %d", u0.iterations, c->sweeps_per_launch);
     int rc;
     if (sched == CLOTHGPU_SCHED_STREAMING) {
         rc = launch_streaming<T>(c, u0, dev_frames);
@@ -348,13 +419,9 @@ int init_state(clothgpu* c, int pos_x, int pos_y) {
 void free_all(clothgpu* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(c->X[i]);
-        cudaFree(c->Y[i]);
-        cudaFree(c->PX[i]);
-        cudaFree(c->PY[i]);
-        cudaFree(c->FL[i]);
-    }
+    for (auto& l : c->link)
+        if (l.on && l.ipc) cudaIpcCloseMemHandle(l.base);
+    cudaFree(c->slab);
     cudaFree(c->ctr);
     cudaFree(c->census);
     cudaFree(c->frames_dev);
@@ -500,12 +567,29 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
         ee = cudaMemset(*p, 0, bytes);
         if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(ee));
     };
-    for (int i = 0; i < 2; ++i) {
-        alloc(&c->X[i], c->plane_elems * c->elem);
-        alloc(&c->Y[i], c->plane_elems * c->elem);
-        alloc(&c->PX[i], c->plane_elems * c->elem);
-        alloc(&c->PY[i], c->plane_elems * c->elem);
-        alloc((void**)&c->FL[i], c->plane_elems);
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            const size_t at = off;
+            off += (bytes + 255) / 256 * 256;
+            return at;
+        };
+        for (int k = 0; k < 8; ++k) c->off_plane[k] = take(c->plane_elems * c->elem);
+        for (int k = 8; k < 10; ++k) c->off_plane[k] = take(c->plane_elems);
+        c->off_slots = take(256);
+        c->slab_bytes = off;
+        alloc(&c->slab, c->slab_bytes);
+        if (rc == CLOTHGPU_OK) {
+            char* b = (char*)c->slab;
+            for (int i = 0; i < 2; ++i) {
+                c->X[i] = b + c->off_plane[0 + i];
+                c->Y[i] = b + c->off_plane[2 + i];
+                c->PX[i] = b + c->off_plane[4 + i];
+                c->PY[i] = b + c->off_plane[6 + i];
+                c->FL[i] = (uint8_t*)(b + c->off_plane[8 + i]);
+            }
+            c->slots = (unsigned int*)(b + c->off_slots);
+        }
     }
     alloc((void**)&c->ctr, sizeof(DevCounters));
     alloc((void**)&c->census, 5 * sizeof(unsigned long long));
@@ -827,6 +911,129 @@ int clothgpu_halo_region(clothgpu* c, int32_t plane, int32_t which, void** dev_p
     *dev_ptr = base + (size_t)row * g.pitch * es;
     *bytes = (size_t)rows * g.pitch * es;
     return CLOTHGPU_OK;
+}
+
+namespace {
+struct StripBlob {  // what a strip tells its neighbours (clothgpu_strip_export)
+    uint32_t magic, version;
+    uint64_t pid;
+    int32_t device;
+    int32_t precision;
+    uint64_t raw_base;  // valid inside the exporting process
+    cudaIpcMemHandle_t ipc;
+    uint64_t off_plane[10];
+    uint64_t off_slots;
+    int64_t cloth_stride;
+    int32_t nx, ny, pitch, ensemble;
+    int32_t held_row0, held_rows, own_row0, own_rows;
+};
+constexpr uint32_t kBlobMagic = 0x434c5347u;  // "CLSG"
+}  // namespace
+
+int clothgpu_strip_export(clothgpu* c, void* blob, size_t cap, size_t* len) {
+    if (int rc = check_handle(c)) return rc;
+    if (!len) return fail(CLOTHGPU_ERR_INVALID, "null len");
+    *len = sizeof(StripBlob);
+    if (!blob) return CLOTHGPU_OK;  // size query
+    if (cap < sizeof(StripBlob)) return fail(CLOTHGPU_ERR_CAPACITY, "blob needs %zu bytes", sizeof(StripBlob));
+    StripBlob b{};
+    b.magic = kBlobMagic;
+    b.version = 1;
+    b.pid = (uint64_t)getpid();
+    b.device = c->device;
+    b.precision = c->precision;
+    b.raw_base = (uint64_t)(uintptr_t)c->slab;
+    CU_TRY(cudaIpcGetMemHandle(&b.ipc, c->slab));
+    for (int k = 0; k < 10; ++k) b.off_plane[k] = c->off_plane[k];
+    b.off_slots = c->off_slots;
+    b.cloth_stride = c->g.cloth_stride;
+    b.nx = c->g.nx, b.ny = c->ny, b.pitch = c->g.pitch, b.ensemble = c->g.ensemble;
+    b.held_row0 = c->g.held_row0, b.held_rows = c->g.held_rows, b.own_row0 = c->g.own_row0, b.own_rows = c->g.own_rows;
+    memcpy(blob, &b, sizeof b);
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_strip_attach(clothgpu* c, const void* up_blob, const void* down_blob) {
+    if (int rc = check_handle(c)) return rc;
+    if (c->desc.strip_rows <= 0) return fail(CLOTHGPU_ERR_STATE, "not a strip handle (desc.strip_rows == 0)");
+    if (attached(c)) return fail(CLOTHGPU_ERR_STATE, "already attached");
+    const Geom& g = c->g;
+    const void* blobs[2] = {up_blob, down_blob};
+    clothgpu::Link links[2];
+    for (int side = 0; side < 2; ++side) {
+        if (!blobs[side]) continue;
+        StripBlob b;
+        memcpy(&b, blobs[side], sizeof b);
+        if (b.magic != kBlobMagic || b.version != 1) return fail(CLOTHGPU_ERR_INVALID, "bad strip blob");
+        if (b.nx != g.nx || b.ny != c->ny || b.pitch != g.pitch || b.ensemble != g.ensemble || b.precision != c->precision)
+            return fail(CLOTHGPU_ERR_INVALID, "neighbour strip belongs to a different cloth (nx/ny/pitch/ensemble/precision)");
+        const int my0 = g.own_row0, my1 = g.own_row0 + g.own_rows;
+        const int p_own0 = b.own_row0, p_own1 = b.own_row0 + b.own_rows;
+        if (side == 0 ? p_own1 != my0 : p_own0 != my1)
+            return fail(CLOTHGPU_ERR_INVALID, "%s neighbour owns rows [%d,%d), mine are [%d,%d): not adjacent",
+                        side == 0 ? "upper" : "lower", p_own0, p_own1, my0, my1);
+        clothgpu::Link& l = links[side];
+        // the neighbour's ghost rows on my side must all be rows I own, and mine must all be rows it owns
+        const int ph0 = b.held_row0, ph1 = b.held_row0 + b.held_rows;
+        l.row_lo = std::max(my0, ph0);
+        l.row_hi = std::min(my1, ph1);
+        const int want = side == 0 ? ph1 - p_own1 : p_own0 - ph0;  // ghost rows the neighbour keeps on my side
+        if (l.row_hi - l.row_lo != want)
+            return fail(CLOTHGPU_ERR_INVALID, "strip of %d rows is thinner than the neighbour's %d ghost rows", g.own_rows, want);
+        const int mine_there = side == 0 ? my0 - g.held_row0 : (g.held_row0 + g.held_rows) - my1;
+        if (mine_there > b.own_rows)
+            return fail(CLOTHGPU_ERR_INVALID, "neighbour strip of %d rows is thinner than my %d ghost rows", b.own_rows, mine_there);
+        if (b.pid == (uint64_t)getpid()) {
+            l.base = (char*)(uintptr_t)b.raw_base;
+            if (b.device != c->device) {
+                int can = 0;
+                CU_TRY(cudaDeviceCanAccessPeer(&can, c->device, b.device));
+                if (!can) return fail(CLOTHGPU_ERR_CUDA, "device %d cannot access device %d", c->device, b.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU_TRY(e);
+                cudaGetLastError();
+            }
+        } else {
+            void* base = nullptr;
+            CU_TRY(cudaIpcOpenMemHandle(&base, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+            l.base = (char*)base;
+            l.ipc = true;
+        }
+        for (int k = 0; k < 10; ++k) l.off_plane[k] = (size_t)b.off_plane[k];
+        l.off_slots = (size_t)b.off_slots;
+        l.cloth_stride = b.cloth_stride;
+        l.held_row0 = b.held_row0;
+        l.held_rows = b.held_rows;
+        l.on = true;
+    }
+    // epoch slots start at 0 (slab is zero-filled at create); make sure nothing is in flight
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->link[0] = links[0];
+    c->link[1] = links[1];
+    c->epoch = 0;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_strip_push(clothgpu* c) {
+    if (int rc = check_handle(c)) return rc;
+    if (!attached(c)) return fail(CLOTHGPU_ERR_STATE, "strip is not attached to its neighbours");
+    if (int rc = strip_begin_op(c)) return rc;
+    auto run = [&](auto tag) -> int {
+        using T = decltype(tag);
+        Planes<T> mine = planes<T>(c, c->cur_pos, c->cur_prev);
+        for (int side = 0; side < 2; ++side) {
+            if (!c->link[side].on) continue;
+            const PeerOut<T> p = peer_out<T>(c, side, c->cur_pos, c->cur_prev);
+            const long long n = (long long)(p.row_hi - p.row_lo) * c->g.pitch;
+            dim3 grid((unsigned)std::min<long long>((n + kStreamThreads - 1) / kStreamThreads, 4096), c->g.ensemble);
+            strip_push_kernel<T><<<grid, kStreamThreads, 0, c->stream>>>(mine, c->g, p);
+            CU_TRY(cudaGetLastError());
+            c->launches++;
+        }
+        return CLOTHGPU_OK;
+    };
+    if (int rc = c->precision == CLOTHGPU_F32 ? run(float{}) : run(double{})) return rc;
+    return strip_end_op(c);
 }
 
 int clothgpu_set_stream(clothgpu* c, void* cuda_stream) {

@@ -22,7 +22,7 @@ EXPORTS = [
     "clothgpu_destroy", "clothgpu_step", "clothgpu_step_n", "clothgpu_step_each", "clothgpu_sync",
     "clothgpu_get_info", "clothgpu_set_schedule", "clothgpu_read_state", "clothgpu_write_state",
     "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_get_counters",
-    "clothgpu_halo_region", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
+    "clothgpu_halo_region", "clothgpu_strip_export", "clothgpu_strip_attach", "clothgpu_strip_push", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
     "clothgpu_last_error", "clothgpu_version",
 ]
 
@@ -64,6 +64,9 @@ def lib():
                                                  C.c_size_t, C.POINTER(C.c_size_t)]
         L.clothgpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.clothgpu_halo_region.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.clothgpu_strip_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.clothgpu_strip_attach.argtypes = [vp, vp, vp]
+        L.clothgpu_strip_push.argtypes = [vp]
         L.clothgpu_set_stream.argtypes = [vp, vp]
         L.clothgpu_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.clothgpu_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -188,6 +191,20 @@ class Cloth:
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         _check(self._L.clothgpu_halo_region(self._h, plane, which, C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
+
+    # row strips over several GPUs (include/clothgpu.h)
+    def strip_export(self):
+        n = C.c_size_t()
+        _check(self._L.clothgpu_strip_export(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(self._L.clothgpu_strip_export(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def strip_attach(self, upper_blob=None, lower_blob=None):
+        _check(self._L.clothgpu_strip_attach(self._h, upper_blob, lower_blob))
+
+    def strip_push(self):
+        _check(self._L.clothgpu_strip_push(self._h))
 
     def last_step_ms(self):
         ms = C.c_float()

@@ -205,7 +205,10 @@ CLOTHGPU_API int clothgpu_set_schedule(clothgpu* c, int32_t schedule);
 CLOTHGPU_API int clothgpu_read_state(clothgpu* c, int32_t cloth, double* x, double* y, double* px, double* py,
                         uint8_t* flags);
 
-/* Inverse of clothgpu_read_state (restore a snapshot / seed a test state).  NULL planes are kept. */
+/* Inverse of clothgpu_read_state (restore a snapshot / seed a test state).  NULL planes are kept.
+ * Coordinates must be finite (|v| <= 1e30), else CLOTHGPU_ERR_INVALID; -0.0 is stored as +0.0 (the update never
+ * produces -0.0 itself).  clothgpu_step rejects non-finite frame values the same way — the Go code would
+ * propagate NaN instead. */
 CLOTHGPU_API int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const double* y,
                          const double* px, const double* py, const uint8_t* flags);
 
@@ -231,6 +234,20 @@ CLOTHGPU_API int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out);
  * plane 0..3 = x,y,px,py, 4 = flags.  `which`: 0 = my top edge rows (to send up), 1 = my bottom
  * edge rows (to send down), 2 = my top ghost rows (to receive), 3 = my bottom ghost rows. */
 CLOTHGPU_API int clothgpu_halo_region(clothgpu* c, int32_t plane, int32_t which, void** dev_ptr, size_t* bytes);
+
+/* ---- one cloth over several GPUs: row strips, one process (or handle) per GPU -------------------------------
+ * No reference counterpart (the reference is single-threaded, main.go:87-100).  Each strip handle is created with
+ * desc.strip_row0/strip_rows; it exports a small blob describing its device memory (clothgpu_strip_export), the
+ * host program passes the blobs of the upper / lower neighbour to clothgpu_strip_attach (any transport: the Python
+ * harness uses torch.distributed all_gather), and from then on clothgpu_step's fused kernel stores the edge rows a
+ * neighbour keeps as ghosts straight into the neighbour's memory (NVLink peer stores) and hand-shakes with
+ * stream-ordered epoch flags — no host round trip, no separate exchange pass.  All strips must issue the same
+ * sequence of clothgpu_step / clothgpu_reset / clothgpu_strip_push calls (they index each other's double buffers).
+ * Blobs from the same process are attached by plain pointer, from other processes through cudaIpcOpenMemHandle. */
+CLOTHGPU_API int clothgpu_strip_export(clothgpu* c, void* blob, size_t cap, size_t* len); /* blob==NULL: size query */
+CLOTHGPU_API int clothgpu_strip_attach(clothgpu* c, const void* upper_blob, const void* lower_blob); /* NULL = cloth edge */
+/* After clothgpu_write_state on attached strips: copy my edge rows into the neighbours' ghost rows. */
+CLOTHGPU_API int clothgpu_strip_push(clothgpu* c);
 
 /* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this handle. */
 CLOTHGPU_API int clothgpu_set_stream(clothgpu* c, void* cuda_stream);

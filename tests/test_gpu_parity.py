@@ -2,6 +2,8 @@
 here, see oracle/cloth_oracle.h "PARITY UNPINNED")."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -291,3 +293,82 @@ def test_full_size_1024_fused_equals_streaming_and_oracle(oracle):
         gs.step(f)
     assert_same_state(gf.read_state(), gs.read_state(), "fused vs streaming after 46 frames")
     assert gf.counters()["relaxations"] == 46 * 8 * (2 * 1024 * 1024 - 2048)
+
+
+@pytest.mark.parametrize("K", [1, 3, 11])
+def test_attached_strips_exchange_inside_the_frame_kernel(oracle, K):
+    """Three strips of one cloth, attached to each other: the fused kernel stores the edge rows into the neighbours'
+    ghost rows itself (same-process attach = plain pointers; other processes use the IPC path, test_strips_multiproc).
+    K = 11 splits the frame into two launches with an exchange after each.  Result == whole cloth, bit for bit."""
+    from clothgpu.strips import StripPlan
+    nx, ny = 150, 132
+    ghost = 2 * K
+    plan = StripPlan(ny, 3, ghost=min(ghost, 16))
+    whole = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K))
+    strips = []
+    for r in range(3):
+        row0, rows = plan.rows(r)
+        strips.append(clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K,
+                                                    strip_row0=row0, strip_rows=rows)))
+    blobs = [s.strip_export() for s in strips]
+    for r, s in enumerate(strips):
+        s.strip_attach(blobs[r - 1] if r > 0 else None, blobs[r + 1] if r < 2 else None)
+    st = random_state(nx, ny, seed=5 + K, pins=0.002)
+    whole.write_state(*st)
+    for r, s in enumerate(strips):
+        row0, rows = plan.rows(r)
+        s.write_state(*[a.reshape(ny, nx)[row0:row0 + rows].ravel() for a in st])
+    for s in strips:
+        s.strip_push()
+    f = _abi.default_frame(K)
+    f.win_w, f.win_h = 3000, 3000
+    f.buttons = MOUSE_DRAGGING
+    f.tear_length = 10.0
+    b1 = plan.bounds[1]
+    f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 500.0, 164.0 + 6 * b1, 495.0, 160.0 + 6 * b1
+    for t in range(5):
+        whole.step(f)
+        for s in strips:
+            s.step(f)
+        parts = [np.concatenate(p) for p in zip(*[s.read_state() for s in strips])]
+        assert_same_state(parts, whole.read_state(), f"attached strips frame {t}")
+    cw = whole.counters()
+    cs = [s.counters() for s in strips]
+    for k in ("live_sticks", "alive_sticks", "relaxations", "torn_last", "inactive"):
+        assert sum(c[k] for c in cs) == cw[k], k
+    with pytest.raises(clothgpu.ClothGpuError):
+        strips[0].set_schedule(SCHED_STREAMING)
+        strips[0].step(f)
+
+
+def _run_strip_worker(nproc, args, timeout=300):
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "strip_worker.py")] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "STRIPS-OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("K", [1, 8])
+def test_strips_multiproc_one_gpu_ipc(K):
+    """Two processes share cuda:0: the neighbour's memory is mapped through cudaIpcOpenMemHandle (the path real
+    multi-GPU runs take), rendezvous over gloo.  Rank 0 compares the gathered strips with the whole cloth."""
+    _run_strip_worker(2, ["--backend", "gloo", "--same-device", "--nx", "200", "--ny", "160", "--iterations", str(K),
+                          "--frames", "6"])
+
+
+def test_strips_multi_gpu_nccl():
+    """One process per GPU over NCCL (rendezvous) + NVLink peer stores; needs >= 2 GPUs."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run_strip_worker(min(n, 8), ["--backend", "nccl", "--nx", "1024", "--ny", "1024", "--iterations", "8", "--frames", "6"])
