@@ -32,6 +32,10 @@ WORKLOADS = {
     "c2": (4096, 4096, 8, 1, "top_row", "BASELINE configs[2] geometry: 4096x4096 cloth, 8 sweeps/frame, f64"),
     "c2k1": (4096, 4096, 1, 1, "top_row", "4096x4096 cloth, 1 sweep/frame (reference semantics), f64"),
     "c3": (128, 128, 8, 2048, "top_row", "BASELINE configs[3] shard: 2048 independent 128x128 cloths per GPU"),
+    # one cloth cut into row strips over the ranks (strong scaling; cloths-per-GPU column = 0 marks the mode)
+    "c4": (16384, 16384, 8, 0, "top_row", "BASELINE configs[4]: one 16384x16384 cloth in row strips over the GPUs, 8 sweeps/frame, f64"),
+    "c4k1": (16384, 16384, 1, 0, "top_row", "one 16384x16384 cloth in row strips over the GPUs, 1 sweep/frame (reference semantics), f64"),
+    "c4s": (4096, 4096, 8, 0, "top_row", "one 4096x4096 cloth in row strips over the GPUs, 8 sweeps/frame, f64"),
 }
 
 
@@ -100,6 +104,18 @@ def make_frame(_abi, wl):
     return f
 
 
+def cpu_desc(_abi, wl, precision):
+    """Descriptor of the CPU arm's sample: ONE cloth of the workload; cloths beyond 2048x2048 are sampled as a
+    2048x2048 cloth of the same spacing/pin rule (per-stick cost does not depend on the size once out of cache)."""
+    nx, ny, K, cloths, pin, _ = WORKLOADS[wl]
+    if nx * ny > 2048 * 2048:
+        nx = ny = 2048
+        return _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, precision=precision, max_iterations=K), nx, ny
+    d = make_desc(_abi, wl, 0, precision)
+    d.ensemble = 1
+    return d, nx, ny
+
+
 def cpu_sample(wl, precision, seconds_target, threads=1):
     """Time the oracle's restatement of the reference CPU path (sequential Gauss-Seidel sweep, AoS +
     pointer layout as in the Go program, 1 thread = the reference's single physics goroutine) on ONE
@@ -107,8 +123,7 @@ def cpu_sample(wl, precision, seconds_target, threads=1):
     import pyoracle
     from clothgpu import _abi
     nx, ny, K, *_ = WORKLOADS[wl]
-    d = make_desc(_abi, wl, 0, precision)
-    d.ensemble = 1
+    d, nx, ny = cpu_desc(_abi, wl, precision)
     o = pyoracle.OracleCloth(d, pyoracle.SEQ_FAITHFUL)
     f = make_frame(_abi, wl)
     o.step(f, threads)                      # warm the caches / page in
@@ -135,8 +150,7 @@ def run_reference(args, rank, world):
     from clothgpu import _abi
     wl = args.workload
     nx, ny, K, cloths, pin, desc_txt = WORKLOADS[wl]
-    d = make_desc(_abi, wl, 0, _abi.F64)
-    d.ensemble = 1
+    d, nx, ny = cpu_desc(_abi, wl, _abi.F64)
     o = pyoracle.OracleCloth(d, pyoracle.SEQ_FAITHFUL)
     f = make_frame(_abi, wl)
     for _ in range(args.warmup):
@@ -219,7 +233,19 @@ def main():
     wl = args.workload
     nx, ny, K, cloths, pin, desc_txt = WORKLOADS[wl]
     precision = _abi.F64 if args.precision == "f64" else _abi.F32
-    cloth = clothgpu.Cloth(make_desc(_abi, wl, local, precision))
+    strips = cloths == 0
+    if strips:
+        # one cloth, row strips: rank r owns rows [bounds[r], bounds[r+1]); edge rows travel inside the fused kernel
+        from clothgpu.strips import StripCloth
+        if world > 1:
+            holder = StripCloth(nx, ny, max_iterations=K, precision=precision, device=local)
+            cloth = holder.cloth
+        else:
+            cloth = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, precision=precision, device=local,
+                                                  max_iterations=K))
+        cloths = 1
+    else:
+        cloth = clothgpu.Cloth(make_desc(_abi, wl, local, precision))
     cloth.set_schedule(_abi.SCHED_FUSED if args.schedule == "fused" else _abi.SCHED_STREAMING)
     stream = torch.cuda.Stream()
     cloth.set_stream(stream.cuda_stream)
@@ -277,9 +303,10 @@ def main():
     # ---- roofline of the dominant kernel (fused_frame_kernel: one launch per step) -----------------------------
     peak, peak_src = peaks()
     bpp = BYTES_PER_PARTICLE_F64 if args.precision == "f64" else BYTES_PER_PARTICLE_F32
-    particles = nx * ny * cloths
+    particles = cloth.nx * cloth.rows * cloths      # per GPU (a strip owns `rows` of the ny rows)
     launches_per_step = launches / args.steps
-    kernel_ms = ms_local / args.steps / max(1.0, (launches_per_step if args.schedule == "fused" else 1.0))
+    fused_per_step = max(1, -(-K // 8)) if args.schedule == "fused" else 1      # handshake kernels are not frame kernels
+    kernel_ms = ms_local / args.steps / fused_per_step
     alg_bytes = bpp * particles * (1.0 if args.schedule == "fused" else 1.0)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -291,12 +318,14 @@ def main():
     line = {
         "metric": "stick_relaxations_per_sec", "value": value, "unit": "stick relaxations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": desc_txt, "nx": nx, "ny": ny, "iterations": K, "pin": pin, "cloths_per_gpu": cloths,
-                   "schedule": args.schedule,
+        "scaling": "strong" if strips else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": desc_txt, "nx": nx, "ny": ny, "iterations": K, "pin": pin,
+                   "cloths_per_gpu": (1.0 / world) if strips else cloths, "schedule": args.schedule,
                    "l2": f"inputs larger than L2: {particles * bpp / 2 / 1e6:.0f} MB of state per GPU, every frame re-streams it",
-                   "sharding": "independent cloths per GPU, no data-path collective"},
-        "frames_per_sec": world * cloths * args.steps / (ms * 1e-3),
+                   "sharding": ("row strips, 2K ghost rows, edge rows stored into the neighbours' memory by the frame kernel "
+                                "(NVLink peer stores + epoch flags), no NCCL on the data path") if strips
+                               else "independent cloths per GPU, no data-path collective"},
+        "frames_per_sec": (1 if strips else world * cloths) * args.steps / (ms * 1e-3),
         "gpu_launches": int(launches),
         "e2e": e2e, "roofline": roofline,
     }
@@ -306,6 +335,8 @@ def main():
         if not args.no_cpu and world >= 1:
             line["cpu_baseline"] = cpu_sample(wl, precision, args.cpu_seconds)
         print(json.dumps(line), flush=True)
+    if strips and world > 1:
+        holder.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
