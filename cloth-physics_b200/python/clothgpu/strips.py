@@ -1,6 +1,6 @@
 """One cloth over several GPUs: row strips, one process per GPU.
 
-`StripPlan` is the partition (pure host logic, also used by the CPU tests with the oracle); `StripCloth`
+`StripPlan` is the partition (pure host logic, also exercised on CPU by tests/test_strips_gloo.py); `StripCloth`
 is one rank's strip on its GPU.  torch.distributed is used for the rendezvous only — an all_gather of the
 small blobs `clothgpu_strip_export` produces.  After `clothgpu_strip_attach` the per-frame exchange is done by
 the fused frame kernel itself: it stores the edge rows a neighbour keeps as ghosts straight into the neighbour's

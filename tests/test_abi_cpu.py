@@ -68,6 +68,6 @@ def test_product_sources_never_reference_the_oracle():
     pkg = os.path.join(ROOT, "cloth-physics_b200")
     for dirpath, _, files in os.walk(pkg):
         for fn in files:
-            if fn.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py", ".go")):
+            if fn.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".cc", ".py", ".go")):
                 src = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "oracle" not in src.lower(), os.path.join(dirpath, fn)

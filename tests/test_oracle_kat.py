@@ -298,3 +298,34 @@ def test_openmp_threads_do_not_change_colour_mode_bits(oracle):
     for u, v in zip(a.read_state(), b.read_state()):
         assert np.array_equal(u, v)
     assert a.relaxations == b.relaxations == 20 * 3 * (2 * 64 * 48 - 64 - 48)
+
+
+def test_colour_vs_sequential_physical_tolerance(oracle):
+    """The stated physical tolerance between the reference's sequential Gauss-Seidel order and the colour order the
+    GPU runs (BASELINE.json north_star), on the hanging default cloth, no mouse, 400 frames.
+    Measured: |delta mean strain| <= 0.027 (the mean strain itself reaches 0.9: one sweep per frame of the reference's
+    soft relaxation lets the cloth stretch a lot), RMS displacement <= 0.50 spacing, max 4.2 spacing."""
+    d = _abi.default_desc()
+    a, b = oracle.OracleCloth(d, oracle.SEQ_FAITHFUL), oracle.OracleCloth(d, oracle.COLOUR)
+    f = _abi.default_frame(1)
+    nx, ny, L = a.nx, a.ny, 6.0
+
+    def mean_strain(st):
+        x, y = st[0].reshape(ny, nx), st[1].reshape(ny, nx)
+        dh = np.hypot(x[:, 1:] - x[:, :-1], y[:, 1:] - y[:, :-1])
+        dv = np.hypot(x[1:] - x[:-1], y[1:] - y[:-1])
+        return (np.concatenate([dh.ravel(), dv.ravel()]) / L - 1.0).mean()
+
+    worst_strain = worst_rms = 0.0
+    for t in range(400):
+        a.step(f)
+        b.step(f)
+        if t % 10 == 9:
+            sa, sb = a.read_state(), b.read_state()
+            disp = np.hypot(sa[0] - sb[0], sa[1] - sb[1]) / L
+            worst_strain = max(worst_strain, abs(mean_strain(sa) - mean_strain(sb)))
+            worst_rms = max(worst_rms, float(np.sqrt((disp ** 2).mean())))
+    assert worst_strain <= 0.05          # absolute difference of mean (d - L)/L
+    assert worst_rms <= 0.75             # in units of the stick rest length
+    assert worst_strain > 0 and worst_rms > 0   # the two orders are genuinely different computations
+    assert a.relaxations == b.relaxations       # same sticks visited (no tearing without a drag)

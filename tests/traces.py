@@ -7,7 +7,8 @@ P, S = EventAdapter.PRIMARY, EventAdapter.SECONDARY
 
 
 def c0_trace(n_frames=1000, iterations=1, scale=1.0, win=(1280, 820), pin_click=(128 + 6 * 40, 164 + 6 * 10)):
-    """frames 0-99 idle; 100-399 slow left-drag sweep with the force ramp; 400-449 released;
+    """frame 2 ctrl-click on particle (40,10) while the cloth is still (almost) at its rest grid, so the click really
+    pins it; frames 3-99 idle; 100-399 slow left-drag sweep with the force ramp; 400-449 released;
     450-549 right-button hold moving along a line (hole punch); 550-599 scroll the focus area to 120;
     600-799 fast zig-zag left-drag (tears); 800 ctrl-click on a particle; then idle."""
     ad = EventAdapter()
@@ -16,7 +17,13 @@ def c0_trace(n_frames=1000, iterations=1, scale=1.0, win=(1280, 820), pin_click=
     for t in range(n_frames):
         if press_frame is not None:
             ad.begin_frame((t - press_frame) / 60.0)
-        if t == 100:
+        if t == 2:
+            ad.press(pin_click[0], pin_click[1], P, ctrl=True)
+            press_frame = t
+        elif t == 3:
+            ad.release()
+            press_frame = None
+        elif t == 100:
             ad.press(300 * scale, 250 * scale, P)
             press_frame = t
         elif 100 < t < 400:
