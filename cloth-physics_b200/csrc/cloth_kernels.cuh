@@ -170,33 +170,37 @@ __global__ void __launch_bounds__(kStreamThreads)
 }
 
 // Census of the owned rows: {live sticks, alive sticks, pinned, inactive, highlighted}.
+// 16 flag bytes per thread and trip (128-bit loads), counted four bytes at a time with byte-parallel masks; padding
+// columns and the spare row hold zero flags, so they add nothing (inactive = existing - active is fixed up by the host
+// side of the sum: the kernel returns the ACTIVE count in slot 3).
 template <typename T>
 __global__ void __launch_bounds__(kStreamThreads)
     count_kernel(Planes<T> P, Geom g, unsigned long long* out5) {
     const int e = blockIdx.y;
-    const long long n = (long long)g.own_rows * g.pitch;
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    unsigned long long live = 0, alive = 0, pinned = 0, inactive = 0, hl = 0;
-    if (i < n) {
-        const int cx = (int)(i % g.pitch);
-        if (cx < g.nx) {
-            const long long at = (long long)e * g.cloth_stride +
-                                 (long long)(g.own_row0 - g.held_row0) * g.pitch + i;
-            const uint32_t f = P.fl[at];
-            pinned = (f & CLOTHGPU_FLAG_PIN) ? 1 : 0;
-            inactive = (f & CLOTHGPU_FLAG_ACTIVE) ? 0 : 1;
-            hl = (f & CLOTHGPU_FLAG_HIGHLIGHT) ? 1 : 0;
-            if (f & CLOTHGPU_FLAG_ALIVE_H) {
-                alive++;
-                if ((f & P.fl[at + 1]) & CLOTHGPU_FLAG_ACTIVE) live++;
-            }
-            if (f & CLOTHGPU_FLAG_ALIVE_V) {
-                alive++;
-                if ((f & P.fl[at + g.pitch]) & CLOTHGPU_FLAG_ACTIVE) live++;
-            }
+    const long long chunks = (long long)g.own_rows * g.pitch / 16;  // pitch is a multiple of 16
+    const uint8_t* base = P.fl + (long long)e * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
+    unsigned int live = 0, alive = 0, pinned = 0, active = 0, hl = 0;
+    constexpr uint32_t k1 = 0x01010101u;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < chunks; c += (long long)gridDim.x * blockDim.x) {
+        const uint4 w4 = *reinterpret_cast<const uint4*>(base + c * 16);
+        const uint4 b4 = *reinterpret_cast<const uint4*>(base + c * 16 + g.pitch);  // the row below (ghost / spare row at the end)
+        const uint32_t nxt = base[c * 16 + 16];                                     // right neighbour of the chunk's last byte
+        const uint32_t w[5] = {w4.x, w4.y, w4.z, w4.w, nxt};
+        const uint32_t bl[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t f = w[q];
+            const uint32_t act = (f >> 1) & k1, ah = (f >> 3) & k1, av = (f >> 4) & k1;
+            const uint32_t act_right = (act >> 8) | ((w[q + 1] >> 1) << 24 & 0x01000000u);
+            const uint32_t act_below = (bl[q] >> 1) & k1;
+            pinned += __popc(f & k1);
+            active += __popc(act);
+            hl += __popc((f >> 2) & k1);
+            alive += __popc(ah) + __popc(av);
+            live += __popc(ah & act & act_right) + __popc(av & act & act_below);  // cloth.go:97
         }
     }
-    unsigned long long v[5] = {live, alive, pinned, inactive, hl};
+    unsigned long long v[5] = {live, alive, pinned, active, hl};
     for (int k = 0; k < 5; k++) {
         const unsigned long long s = block_sum_ull(v[k]);
         if (threadIdx.x == 0 && s) atomicAdd(&out5[k], s);

@@ -16,6 +16,7 @@
 
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
+#include "cloth_stream1.cuh"
 #include "frame_fold.h"
 
 using namespace clothgpu_impl;
@@ -80,6 +81,8 @@ struct clothgpu {
     int forced_tile_rows = 0;
     int fused_variant = -1;  // -1: chosen per launch (choose_variant); >= 0: forced, see launch_fused
     int sweeps_per_launch = kMaxSweepsPerLaunch;
+    int k1_stream = 1;       // 1: frames with one sweep take the register-streaming kernel (cloth_stream1.cuh)
+    int s1_chunk_rows = 0;   // 0: chosen per launch
     // All state planes and the strip epoch slots live in ONE device allocation, so a neighbouring strip (another
     // process, another GPU) maps everything with a single cudaIpcMemHandle.
     void* slab = nullptr;
@@ -305,6 +308,51 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     return strip_end_op(c);
 }
 
+// One sweep per frame (the reference's own semantics): the register-streaming kernel, one pass over HBM.
+template <typename T>
+int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
+    const Geom& g = c->g;
+    Stream1Plan pl{};
+    pl.windows = g.nx <= 64 ? 1 : (g.nx - 64 + kS1WindowStep - 1) / kS1WindowStep + 1;
+    // Row chunks.  Warps are independent and equally loaded, so the launch runs in "waves" of `slots` resident warps
+    // (16 per SM at 128 registers): long chunks amortise the 4 halo rows, but the task count should be just under a
+    // whole number of waves.  With many waves the last, partial one no longer matters and 128-row chunks are used.
+    const long long slots = (long long)c->sm_count * 16;
+    const long long per_chunk = (long long)pl.windows * g.ensemble;  // tasks added by one more chunk
+    int R = c->s1_chunk_rows;
+    if (R < 2) {
+        R = 128;
+        const double waves = (double)(per_chunk * ((g.own_rows + R - 1) / R)) / (double)slots;
+        if (waves < 6.0) {
+            const long long w = std::max<long long>(1, (long long)(waves + 0.5));
+            const long long chunks = std::max<long long>(1, w * slots / per_chunk);
+            R = (int)((g.own_rows + chunks - 1) / chunks);
+            R = std::max(8, (R + 1) & ~1);
+        }
+    }
+    pl.chunk_rows = R;
+    pl.chunks = (g.own_rows + R - 1) / R;
+    pl.tasks = (long long)pl.windows * pl.chunks * g.ensemble;
+    const int nxt = c->cur_pos ^ 1, nprev = c->cur_prev ^ 1;
+    Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
+    Planes<T> out = planes<T>(c, nxt, nprev);
+    const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
+    if (int rc = strip_begin_op(c)) return rc;
+    const unsigned blocks = (unsigned)((pl.tasks + kS1Threads / 32 - 1) / (kS1Threads / 32));
+    const bool pc = per_cloth != nullptr;
+    if (pc)
+        stream1_frame_kernel<T, true, true><<<blocks, kS1Threads, 0, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+    else if (u.buttons & CLOTHGPU_MOUSE_DRAGGING)
+        stream1_frame_kernel<T, false, true><<<blocks, kS1Threads, 0, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+    else
+        stream1_frame_kernel<T, false, false><<<blocks, kS1Threads, 0, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    c->cur_pos = nxt;
+    c->cur_prev = nprev;
+    return strip_end_op(c);
+}
+
 template <typename T>
 int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     const Geom& g = c->g;
@@ -384,6 +432,10 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     int rc;
     if (sched == CLOTHGPU_SCHED_STREAMING) {
         rc = launch_streaming<T>(c, u0, dev_frames);
+    } else if (u0.iterations == 1 && c->k1_stream &&
+               (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble >= 2ll * c->sm_count) {
+        // (small cloths cannot feed enough independent warps; they take the tile kernel below)
+        rc = launch_stream1<T>(c, u0, dev_frames);
     } else {
         int left = u0.iterations, first = 1;
         rc = CLOTHGPU_OK;
@@ -549,6 +601,8 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     c->plane_elems = (size_t)g.cloth_stride * ensemble;
     if (const char* s = getenv("CLOTHGPU_TILE_ROWS")) c->forced_tile_rows = atoi(s);
     if (const char* s = getenv("CLOTHGPU_FUSED_VARIANT")) c->fused_variant = atoi(s);
+    if (const char* s = getenv("CLOTHGPU_K1_STREAM")) c->k1_stream = atoi(s);
+    if (const char* s = getenv("CLOTHGPU_S1_ROWS")) c->s1_chunk_rows = atoi(s) & ~1;
     if (const char* s = getenv("CLOTHGPU_SWEEPS_PER_LAUNCH")) {
         const int v = atoi(s);
         if (v >= 1 && v <= kMaxSweepsPerLaunch) c->sweeps_per_launch = v;
@@ -862,8 +916,8 @@ int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
     if (!out) return fail(CLOTHGPU_ERR_INVALID, "null out");
     const Geom& g = c->g;
     CU_TRY(cudaMemsetAsync(c->census, 0, 5 * sizeof(unsigned long long), c->stream));
-    const long long n = (long long)g.own_rows * g.pitch;
-    dim3 grid((unsigned)((n + kStreamThreads - 1) / kStreamThreads), g.ensemble);
+    const long long chunks = (long long)g.own_rows * g.pitch / 16;
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((chunks + kStreamThreads - 1) / kStreamThreads, c->sm_count * 4)), g.ensemble);
     if (c->precision == CLOTHGPU_F32)
         count_kernel<float><<<grid, kStreamThreads, 0, c->stream>>>(planes<float>(c, c->cur_pos, c->cur_prev), g, c->census);
     else
@@ -875,6 +929,7 @@ int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
     CU_TRY(cudaMemcpyAsync(h5, c->census, sizeof h5, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemcpyAsync(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    h5[3] = (unsigned long long)g.nx * g.own_rows * g.ensemble - h5[3];  // the kernel counts ACTIVE particles
     out->frames = c->frames;
     out->live_sticks = h5[0];
     out->alive_sticks = h5[1];
