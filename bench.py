@@ -32,6 +32,9 @@ WORKLOADS = {
     "c2": (4096, 4096, 8, 1, "top_row", "BASELINE configs[2] geometry: 4096x4096 cloth, 8 sweeps/frame, f64"),
     "c2k1": (4096, 4096, 1, 1, "top_row", "4096x4096 cloth, 1 sweep/frame (reference semantics), f64"),
     "c3": (128, 128, 8, 2048, "top_row", "BASELINE configs[3] shard: 2048 independent 128x128 cloths per GPU"),
+    # BASELINE configs[2]: scripted drag / tear / hole-punch trace, live-stick compaction after every frame
+    "c2t": (4096, 4096, 1, 1, "top_row", "BASELINE configs[2]: 4096x4096 cloth, scripted drag/tear/hole-punch trace, live-stick compaction every frame, 1 sweep/frame, f64"),
+    "c2t8": (4096, 4096, 8, 1, "top_row", "BASELINE configs[2]: 4096x4096 cloth, scripted drag/tear/hole-punch trace, live-stick compaction every frame, 8 sweeps/frame, f64"),
     # one cloth cut into row strips over the ranks (strong scaling; cloths-per-GPU column = 0 marks the mode)
     "c4": (16384, 16384, 8, 0, "top_row", "BASELINE configs[4]: one 16384x16384 cloth in row strips over the GPUs, 8 sweeps/frame, f64"),
     "c4k1": (16384, 16384, 1, 0, "top_row", "one 16384x16384 cloth in row strips over the GPUs, 1 sweep/frame (reference semantics), f64"),
@@ -45,6 +48,16 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_facts(workload):
+    """Per-launch DRAM traffic and f64-pipe utilisation of the dominant kernel, from the committed ncu --set full captures
+    (profiles/ncu_facts.json; the capture file is named there).  Not measured live: ncu cannot run inside a bench."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_facts.json")) as f:
+            return json.load(f).get(workload) or {}
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -250,11 +263,28 @@ def main():
     stream = torch.cuda.Stream()
     cloth.set_stream(stream.cuda_stream)
     frame = make_frame(_abi, wl)
-    frames_w = clothgpu.frame_array([frame] * args.warmup)
-    frames_t = clothgpu.frame_array([frame] * args.steps)
+    traced = wl.startswith("c2t")
+    if traced:
+        # the c0 trace scaled x24 to the 4096^2 cloth: frames 380.. cover the end of the slow drag, the
+        # release, the right-button hole punch with a moving focus area, the scroll and (for long runs) the fast zig-zag
+        from traces import c0_trace
+        tr = c0_trace(380 + args.warmup + args.steps, iterations=K, scale=24.0, win=(frame.win_w, frame.win_h))[380:]
+        frames_w = clothgpu.frame_array(tr[:args.warmup])
+        frames_t = clothgpu.frame_array(tr[args.warmup:])
+    else:
+        frames_w = clothgpu.frame_array([frame] * args.warmup)
+        frames_t = clothgpu.frame_array([frame] * args.steps)
+
+    def run_frames(arr):
+        if not traced:
+            cloth.step_n(arr)
+            return
+        for i in range(len(arr)):            # tear mask update + compaction of the live-stick list, all on the device
+            cloth.step(arr[i])
+            cloth.compact_segments()
 
     # ---- device-resident throughput: K steps back to back, state already in HBM --------------------------
-    cloth.step_n(frames_w)
+    run_frames(frames_w)
     cloth.sync()
     c0 = cloth.counters()
     l0 = cloth.launch_count()
@@ -263,7 +293,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             ev0.record(stream)
-            cloth.step_n(frames_t)
+            run_frames(frames_t)
             ev1.record(stream)
         ev1.synchronize()
         barrier()
@@ -286,8 +316,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0 = cloth.counters()["relaxations"]
         e0.record(stream)
-        for _ in range(n_e2e):
-            cloth.step(frame)
+        for i in range(n_e2e):
+            cloth.step(frames_t[i % len(frames_t)] if traced else frame)
+            if traced:
+                live_n = cloth.count_segments()      # compaction + the live-stick count back on the host
             last = cloth.counters()
         e1.record(stream)
     e1.synchronize()
@@ -298,7 +330,12 @@ def main():
     e2e = {"value": e2e_relax / (e2e_ms * 1e-3), "unit": "stick relaxations/s",
            "h2d_bytes_per_step": C.sizeof(_abi.Frame), "d2h_bytes_per_step": C.sizeof(_abi.Counters),
            "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
-           "what": "clothgpu_step(host frame) + clothgpu_get_counters (sync D2H) per frame"}
+           "what": "clothgpu_step(host frame) + " + ("live-stick compaction + count (8 B D2H) + " if traced else "") +
+                   "clothgpu_get_counters (sync D2H) per frame"}
+    if traced:
+        line_extra = {"live_sticks_end": live_n, "alive_sticks_end": last["alive_sticks"], "inactive_end": last["inactive"]}
+    else:
+        line_extra = {}
 
     # ---- roofline of the dominant kernel (fused_frame_kernel: one launch per step) -----------------------------
     peak, peak_src = peaks()
@@ -306,14 +343,32 @@ def main():
     particles = cloth.nx * cloth.rows * cloths      # per GPU (a strip owns `rows` of the ny rows)
     launches_per_step = launches / args.steps
     fused_per_step = max(1, -(-K // 8)) if args.schedule == "fused" else 1      # handshake kernels are not frame kernels
+    if traced:
+        # the frame kernel alone: time the same frames again without the compaction launches
+        cloth.reset(128, 164)
+        cloth.step_n(frames_w)
+        with torch.cuda.stream(stream):
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            cloth.step_n(frames_t)
+            k1.record(stream)
+        k1.synchronize()
+        ms_local = k0.elapsed_time(k1)
     kernel_ms = ms_local / args.steps / fused_per_step
     alg_bytes = bpp * particles * (1.0 if args.schedule == "fused" else 1.0)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    suffix = "<double>" if args.precision == "f64" else "<float>"
+    kernel = ("stream1_frame_kernel" if (K == 1 and args.schedule == "fused" and nx * ny >= 256 * 256) else
+              "fused_frame_kernel" if args.schedule == "fused" else "relax_pass_kernel") + suffix
+    facts = ncu_facts(wl if args.precision == "f64" and args.schedule == "fused" else None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "fused_frame_kernel<double>" if args.precision == "f64" else "fused_frame_kernel<float>",
+                "traffic": facts.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": kernel,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "compulsory bytes (65.1 B/particle/frame, independent of the sweep count) / launch time; "
-                        "with 8 binary64 sweeps per frame the kernel is fp64-pipe bound, see DESIGN.md"}
+                "fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct"),
+                "ncu_source": facts.get("source"),
+                "note": "achieved = compulsory bytes (65.1 B/particle/frame in f64, independent of the sweep count) / launch time. "
+                        "With 8 binary64 sweeps per frame the kernel is bound by the f64 pipe (fp64_pipe_active_pct, from the ncu "
+                        "capture named in ncu_source), with 1 sweep by HBM; see DESIGN.md §3"}
 
     line = {
         "metric": "stick_relaxations_per_sec", "value": value, "unit": "stick relaxations/s", "n_gpus": world,
@@ -329,6 +384,7 @@ def main():
         "gpu_launches": int(launches),
         "e2e": e2e, "roofline": roofline,
     }
+    line.update(line_extra)
 
     if rank == 0:
         line["clocks"] = clk.summary()

@@ -858,11 +858,10 @@ int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* act
     return CLOTHGPU_OK;
 }
 
-int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
-                               uint32_t* sticks_idx, size_t cap, size_t* n_out) {
-    if (int rc = check_handle(c)) return rc;
+namespace {
+// Live-stick compaction on the handle's stream: per-block counts, exclusive scan, ballot-ranked scatter into c->seg_out.
+int compact_enqueue(clothgpu* c, int32_t cloth, size_t* max_sticks_out) {
     if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
-    if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
     const Geom& g = c->g;
     const long long n = (long long)g.nx * g.own_rows;
     const unsigned blocks = (unsigned)((n + kStreamThreads - 1) / kStreamThreads);
@@ -883,25 +882,43 @@ int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t*
     float4* d_xyxy = (float4*)c->seg_out;
     uint2* d_idx = (uint2*)(d_xyxy + max_sticks);
     uint8_t* d_hl = (uint8_t*)(d_idx + max_sticks);
-    if (c->precision == CLOTHGPU_F32) {
-        Planes<float> P = planes<float>(c, c->cur_pos, c->cur_prev);
-        segment_count_kernel<float><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        Planes<T> P = planes<T>(c, c->cur_pos, c->cur_prev);
+        segment_count_kernel<T><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
         segment_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_counts, (int)blocks, c->seg_total);
-        segment_write_kernel<float><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy,
-                                                                             d_hl, d_idx, max_sticks);
-    } else {
-        Planes<double> P = planes<double>(c, c->cur_pos, c->cur_prev);
-        segment_count_kernel<double><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
-        segment_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_counts, (int)blocks, c->seg_total);
-        segment_write_kernel<double><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy,
-                                                                              d_hl, d_idx, max_sticks);
-    }
+        segment_write_kernel<T><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy, d_hl, d_idx, max_sticks);
+    };
+    if (c->precision == CLOTHGPU_F32)
+        run(float{});
+    else
+        run(double{});
     CU_TRY(cudaGetLastError());
     c->launches += 3;
+    if (max_sticks_out) *max_sticks_out = max_sticks;
+    return CLOTHGPU_OK;
+}
+}  // namespace
+
+int clothgpu_compact_segments(clothgpu* c, int32_t cloth) {
+    if (int rc = check_handle(c)) return rc;
+    return compact_enqueue(c, cloth, nullptr);
+}
+
+int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
+                               uint32_t* sticks_idx, size_t cap, size_t* n_out) {
+    if (int rc = check_handle(c)) return rc;
+    if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
+    size_t max_sticks = 0;
+    if (int rc = compact_enqueue(c, cloth, &max_sticks)) return rc;
+    float4* d_xyxy = (float4*)c->seg_out;
+    uint2* d_idx = (uint2*)(d_xyxy + max_sticks);
+    uint8_t* d_hl = (uint8_t*)(d_idx + max_sticks);
     unsigned long long total = 0;
     CU_TRY(cudaMemcpyAsync(&total, c->seg_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     *n_out = (size_t)total;
+    if (!xyxy && !highlighted && !sticks_idx) return CLOTHGPU_OK;  // count only
     if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
     if (total) {
         if (xyxy) CU_TRY(cudaMemcpy(xyxy, d_xyxy, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost));

@@ -227,6 +227,12 @@ CLOTHGPU_API int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, 
 CLOTHGPU_API int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
                                uint32_t* sticks_idx, size_t cap, size_t* n);
 
+/* Only the device half of the above: build the compacted live-stick list of cloth `cloth` in device memory,
+ * asynchronously on the handle's stream (the next clothgpu_read_segments_f32 re-runs it; with all three output
+ * pointers NULL that call returns just the count).  Lets a renderer that consumes the list on the GPU, or a benchmark
+ * of the tear + compaction path (BASELINE.json configs[2]), avoid the host copy. */
+CLOTHGPU_API int clothgpu_compact_segments(clothgpu* c, int32_t cloth);
+
 /* Counters after the last queued frame (synchronises). */
 CLOTHGPU_API int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out);
 
