@@ -424,17 +424,22 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         dev_frames = (const FrameU<T>*)c->frames_dev;
     }
     CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, sizeof(unsigned long long), c->stream));
-    int sched = c->schedule == CLOTHGPU_SCHED_AUTO ? CLOTHGPU_SCHED_FUSED : c->schedule;
-    if (attached(c) && sched != CLOTHGPU_SCHED_FUSED)
+    int sched = c->schedule;
+    if (sched == CLOTHGPU_SCHED_AUTO) {
+        // small cloths cannot feed enough independent warps to the row-streaming kernel; they take the tile kernel
+        const long long warps = (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble;
+        sched = (u0.iterations == 1 && c->k1_stream && warps >= 2ll * c->sm_count) ? CLOTHGPU_SCHED_ROWSTREAM : CLOTHGPU_SCHED_FUSED;
+    } else if (sched == CLOTHGPU_SCHED_ROWSTREAM && u0.iterations != 1) {
+        sched = CLOTHGPU_SCHED_FUSED;
+    }
+    if (attached(c) && sched == CLOTHGPU_SCHED_STREAMING)
         return fail(CLOTHGPU_ERR_STATE, "attached strips exchange their edge rows inside the fused kernel; the streaming schedule is for detached handles");
-    if (c->desc.strip_rows > 0 && !attached(c) && sched == CLOTHGPU_SCHED_FUSED && u0.iterations > c->sweeps_per_launch)
+    if (c->desc.strip_rows > 0 && !attached(c) && sched != CLOTHGPU_SCHED_STREAMING && u0.iterations > c->sweeps_per_launch)
         return fail(CLOTHGPU_ERR_STATE, "a detached strip cannot split %d sweeps over several launches (ghost rows would go stale between launches); attach the neighbours or use <= %d", u0.iterations, c->sweeps_per_launch);
     int rc;
     if (sched == CLOTHGPU_SCHED_STREAMING) {
         rc = launch_streaming<T>(c, u0, dev_frames);
-    } else if (u0.iterations == 1 && c->k1_stream &&
-               (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble >= 2ll * c->sm_count) {
-        // (small cloths cannot feed enough independent warps; they take the tile kernel below)
+    } else if (sched == CLOTHGPU_SCHED_ROWSTREAM) {
         rc = launch_stream1<T>(c, u0, dev_frames);
     } else {
         int left = u0.iterations, first = 1;
@@ -751,7 +756,7 @@ int clothgpu_get_info(clothgpu* c, clothgpu_info* info) {
 
 int clothgpu_set_schedule(clothgpu* c, int32_t schedule) {
     if (!c) return fail(CLOTHGPU_ERR_INVALID, "null handle");
-    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_FUSED)
+    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_ROWSTREAM)
         return fail(CLOTHGPU_ERR_INVALID, "unknown schedule %d", schedule);
     c->schedule = schedule;
     return CLOTHGPU_OK;

@@ -61,9 +61,11 @@ typedef enum clothgpu_precision {
 
 /* Kernel schedule used by clothgpu_step.  All schedules produce bit-identical results. */
 typedef enum clothgpu_schedule {
-    CLOTHGPU_SCHED_AUTO = 0,
-    CLOTHGPU_SCHED_STREAMING = 1, /* one Verlet launch + one launch per colour pass (4*K)            */
-    CLOTHGPU_SCHED_FUSED = 2      /* one launch per frame: shared-memory tiles with 2*K halos        */
+    CLOTHGPU_SCHED_AUTO = 0,      /* ROWSTREAM for one-sweep frames of cloths large enough to feed it, else FUSED */
+    CLOTHGPU_SCHED_STREAMING = 1, /* one Verlet launch + one launch per colour pass (4*K), in place   */
+    CLOTHGPU_SCHED_FUSED = 2,     /* one launch per frame: shared-memory tiles with 2*K halos        */
+    CLOTHGPU_SCHED_ROWSTREAM = 3  /* one launch per frame, iterations == 1 only: every warp streams a 64-column window
+                                     down the rows in registers (frames with more sweeps fall back to FUSED) */
 } clothgpu_schedule;
 
 /* Bits of the per-particle flag byte (also the layout returned by clothgpu_read_flags). */

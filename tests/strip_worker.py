@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--ny", type=int, default=256)
     ap.add_argument("--iterations", type=int, default=1)
     ap.add_argument("--frames", type=int, default=4)
+    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream"])
     a = ap.parse_args()
 
     import torch
@@ -58,11 +59,14 @@ def main():
     f.buttons = _abi.MOUSE_DRAGGING
     f.tear_length = 11.0
 
+    sched = {"auto": _abi.SCHED_AUTO, "fused": _abi.SCHED_FUSED, "rowstream": _abi.SCHED_ROWSTREAM}[a.schedule]
     s = StripCloth(a.nx, a.ny, max_iterations=K, device=dev)
+    s.cloth.set_schedule(sched)
     s.write_state(x, y, px, py, fl)
     whole = None
     if rank == 0:
         whole = clothgpu.Cloth(_abi.grid_desc(a.nx, a.ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K, device=dev))
+        whole.set_schedule(sched)
         whole.write_state(x, y, px, py, fl)
     ok = True
     for t in range(a.frames):

@@ -10,7 +10,7 @@ import pytest
 import clothgpu
 from clothgpu import _abi
 from clothgpu._abi import (FLAG_ACTIVE, FLAG_ALIVE_H, FLAG_ALIVE_V, FLAG_HIGHLIGHT, FLAG_PIN, MOUSE_DRAGGING,
-                           SCHED_FUSED, SCHED_STREAMING)
+                           SCHED_FUSED, SCHED_ROWSTREAM, SCHED_STREAMING)
 from traces import c0_trace
 
 pytestmark = pytest.mark.gpu
@@ -51,7 +51,7 @@ def make_pair(oracle, desc, schedule):
     return g, o
 
 
-@pytest.mark.parametrize("schedule", [SCHED_STREAMING, SCHED_FUSED])
+@pytest.mark.parametrize("schedule", [SCHED_STREAMING, SCHED_FUSED, SCHED_ROWSTREAM])
 def test_default_cloth_scripted_trace_bit_exact(oracle, schedule):
     """BASELINE configs[0]: the reference's default GUI cloth, 1000 frames, drag / hole / tear / ctrl-pin."""
     desc = _abi.default_desc()
@@ -94,7 +94,7 @@ def test_random_states_bit_exact(oracle, nx, ny, K):
     f.tear_length = 9.5                                           # low threshold: many tears
     f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 128.0 + 3 * nx, 164.0 + 3 * ny, 120.0 + 3 * nx, 170.0 + 3 * ny
     results = []
-    for schedule in (SCHED_STREAMING, SCHED_FUSED):
+    for schedule in (SCHED_STREAMING, SCHED_FUSED) + ((SCHED_ROWSTREAM,) if K == 1 else ()):
         g, o = make_pair(oracle, desc, schedule)
         g.write_state(*st)
         o.write_state(*st)
@@ -172,10 +172,12 @@ def test_live_stick_list_matches_reference_render_order(oracle):
     assert np.all(idx[:, 1] > idx[:, 0])
 
 
-def test_ensemble_cloths_are_independent(oracle):
+@pytest.mark.parametrize("K,schedule", [(8, SCHED_FUSED), (1, SCHED_FUSED), (1, SCHED_ROWSTREAM)])
+def test_ensemble_cloths_are_independent(oracle, K, schedule):
     nx, ny, E = 128, 128, 5
-    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, ensemble=E)
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, ensemble=E, max_iterations=K)
     g = clothgpu.Cloth(desc)
+    g.set_schedule(schedule)
     one = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW)
     oracles = [oracle.OracleCloth(one, oracle.COLOUR) for _ in range(E)]
     for e in range(E):
@@ -184,7 +186,7 @@ def test_ensemble_cloths_are_independent(oracle):
         oracles[e].write_state(*st)
     frames = []
     for e in range(E):
-        f = _abi.default_frame(8)
+        f = _abi.default_frame(K)
         f.win_w, f.win_h = 2000, 2000
         f.buttons = MOUSE_DRAGGING if e % 2 else 0
         f.mouse_x, f.mouse_y = 128.0 + 40 * e, 300.0
@@ -232,8 +234,8 @@ def _exchange_halos_same_device(upper, lower):
         assert rt.cudaMemcpy(dst, src, n, 3) == 0
 
 
-@pytest.mark.parametrize("schedule", [SCHED_STREAMING, SCHED_FUSED])
-@pytest.mark.parametrize("K", [1, 3])
+@pytest.mark.parametrize("schedule,K", [(SCHED_STREAMING, 1), (SCHED_STREAMING, 3), (SCHED_FUSED, 1), (SCHED_FUSED, 3),
+                                        (SCHED_ROWSTREAM, 1)])
 def test_two_row_strips_equal_whole_cloth(oracle, schedule, K):
     """Strip decomposition is exact: 2 strips + ghost-row exchange == whole cloth, bit for bit."""
     nx, ny, split = 140, 120, 64
@@ -295,8 +297,8 @@ def test_full_size_1024_fused_equals_streaming_and_oracle(oracle):
     assert gf.counters()["relaxations"] == 46 * 8 * (2 * 1024 * 1024 - 2048)
 
 
-@pytest.mark.parametrize("K", [1, 3, 11])
-def test_attached_strips_exchange_inside_the_frame_kernel(oracle, K):
+@pytest.mark.parametrize("K,schedule", [(1, SCHED_FUSED), (1, SCHED_ROWSTREAM), (3, SCHED_FUSED), (11, SCHED_FUSED)])
+def test_attached_strips_exchange_inside_the_frame_kernel(oracle, K, schedule):
     """Three strips of one cloth, attached to each other: the fused kernel stores the edge rows into the neighbours'
     ghost rows itself (same-process attach = plain pointers; other processes use the IPC path, test_strips_multiproc).
     K = 11 splits the frame into two launches with an exchange after each.  Result == whole cloth, bit for bit."""
@@ -313,6 +315,8 @@ def test_attached_strips_exchange_inside_the_frame_kernel(oracle, K):
     blobs = [s.strip_export() for s in strips]
     for r, s in enumerate(strips):
         s.strip_attach(blobs[r - 1] if r > 0 else None, blobs[r + 1] if r < 2 else None)
+        s.set_schedule(schedule)
+    whole.set_schedule(schedule)
     st = random_state(nx, ny, seed=5 + K, pins=0.002)
     whole.write_state(*st)
     for r, s in enumerate(strips):
@@ -357,12 +361,12 @@ def _run_strip_worker(nproc, args, timeout=300):
     assert "STRIPS-OK" in r.stdout, r.stdout[-3000:]
 
 
-@pytest.mark.parametrize("K", [1, 8])
-def test_strips_multiproc_one_gpu_ipc(K):
+@pytest.mark.parametrize("K,schedule", [(1, "fused"), (1, "rowstream"), (8, "fused")])
+def test_strips_multiproc_one_gpu_ipc(K, schedule):
     """Two processes share cuda:0: the neighbour's memory is mapped through cudaIpcOpenMemHandle (the path real
     multi-GPU runs take), rendezvous over gloo.  Rank 0 compares the gathered strips with the whole cloth."""
     _run_strip_worker(2, ["--backend", "gloo", "--same-device", "--nx", "200", "--ny", "160", "--iterations", str(K),
-                          "--frames", "6"])
+                          "--frames", "6", "--schedule", schedule])
 
 
 def test_strips_multi_gpu_nccl():
