@@ -197,7 +197,8 @@ def main():
     ap.add_argument("--impl", default="clothgpu", choices=["clothgpu", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--schedule", default="fused", choices=["fused", "streaming"])
+    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream", "streaming"],
+                    help="auto = what clothgpu_step picks itself: the row-streaming kernel for one-sweep frames, the tile kernel otherwise")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extras", action="store_true", help="also time the K=1 and L2-resident variants")
@@ -259,7 +260,8 @@ def main():
         cloths = 1
     else:
         cloth = clothgpu.Cloth(make_desc(_abi, wl, local, precision))
-    cloth.set_schedule(_abi.SCHED_FUSED if args.schedule == "fused" else _abi.SCHED_STREAMING)
+    cloth.set_schedule({"auto": _abi.SCHED_AUTO, "fused": _abi.SCHED_FUSED, "rowstream": _abi.SCHED_ROWSTREAM,
+                        "streaming": _abi.SCHED_STREAMING}[args.schedule])
     stream = torch.cuda.Stream()
     cloth.set_stream(stream.cuda_stream)
     frame = make_frame(_abi, wl)
@@ -342,7 +344,7 @@ def main():
     bpp = BYTES_PER_PARTICLE_F64 if args.precision == "f64" else BYTES_PER_PARTICLE_F32
     particles = cloth.nx * cloth.rows * cloths      # per GPU (a strip owns `rows` of the ny rows)
     launches_per_step = launches / args.steps
-    fused_per_step = max(1, -(-K // 8)) if args.schedule == "fused" else 1      # handshake kernels are not frame kernels
+    fused_per_step = max(1, -(-K // 8)) if args.schedule != "streaming" else 1      # handshake kernels are not frame kernels
     if traced:
         # the frame kernel alone: time the same frames again without the compaction launches
         cloth.reset(128, 164)
@@ -355,12 +357,12 @@ def main():
         k1.synchronize()
         ms_local = k0.elapsed_time(k1)
     kernel_ms = ms_local / args.steps / fused_per_step
-    alg_bytes = bpp * particles * (1.0 if args.schedule == "fused" else 1.0)
+    alg_bytes = bpp * particles
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     suffix = "<double>" if args.precision == "f64" else "<float>"
-    kernel = ("stream1_frame_kernel" if (K == 1 and args.schedule == "fused" and nx * ny >= 256 * 256) else
-              "fused_frame_kernel" if args.schedule == "fused" else "relax_pass_kernel") + suffix
-    facts = ncu_facts(wl if args.precision == "f64" and args.schedule == "fused" else None)
+    kernel = ("stream1_frame_kernel" if (K == 1 and (args.schedule == "rowstream" or (args.schedule == "auto" and nx * ny * cloths >= 256 * 256))) else
+              "fused_frame_kernel" if args.schedule != "streaming" else "relax_pass_kernel") + suffix
+    facts = ncu_facts(wl if args.precision == "f64" and args.schedule == "auto" else None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": facts.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": kernel,
                 "algorithmic_bytes_per_launch": alg_bytes,

@@ -252,18 +252,42 @@ __device__ __forceinline__ int tail_sticks(const Planes<T>& P, const Geom& g, lo
     return (int)v_live + (int)h_live;
 }
 
+// Sticks per block of kSegBlock consecutive particles of the owned rows in PADDED row-major order (padding columns
+// hold zero flags and add nothing, so the order of the listed sticks is the unpadded one).  16 flag bytes per thread,
+// byte-parallel tests: tail t lists its vertical stick when t and the particle above are active and that particle's
+// ALIVE_V bit is set, its horizontal stick likewise with the particle to the left.
+constexpr int kSegPerThread = 16;
+constexpr int kSegBlock = kStreamThreads * kSegPerThread;
+
 template <typename T>
 __global__ void __launch_bounds__(kStreamThreads)
     segment_count_kernel(Planes<T> P, Geom g, int cloth, unsigned int* __restrict__ block_counts) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = (long long)g.own_rows * g.nx;
-    unsigned long long c = 0;
-    if (i < n) {
-        bool v, h;
-        c = tail_sticks(P, g, (long long)cloth * g.cloth_stride, (int)(i / g.nx), (int)(i % g.nx), v, h);
+    const long long chunks = (long long)g.own_rows * g.pitch / 16;
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const uint8_t* base = P.fl + (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
+    unsigned long long n = 0;
+    if (c < chunks) {
+        constexpr uint32_t k1 = 0x01010101u;
+        const long long off = c * 16;
+        const int ly = (int)(off / g.pitch), cx = (int)(off - (long long)ly * g.pitch);
+        const uint4 w4 = *reinterpret_cast<const uint4*>(base + off);
+        uint4 u4 = make_uint4(0, 0, 0, 0);  // the row above: a ghost row of a strip, or absent at the cloth's top
+        if (g.own_row0 + ly > g.held_row0) u4 = *reinterpret_cast<const uint4*>(base + off - g.pitch);
+        const uint32_t left = cx > 0 ? base[off - 1] : 0u;
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
+        uint32_t carry = left;  // flag byte of the particle left of word q
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t f = w[q], act = (f >> 1) & k1;
+            const uint32_t fl_left = (f << 8) | (carry & 0xffu);  // each byte: the flags of its left neighbour
+            const uint32_t v = act & (up[q] >> 4) & (up[q] >> 1) & k1;
+            const uint32_t h = act & (fl_left >> 3) & (fl_left >> 1) & k1;
+            n += __popc(v) + __popc(h);
+            carry = f >> 24;
+        }
     }
-    const unsigned long long s = block_sum_ull(c);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned int)s;
+    const unsigned long long s = block_sum_ull(n);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned int)s;  // 256 threads x 16 particles = one scatter block
 }
 
 // exclusive scan of block_counts in place (single block); total -> *total_out
@@ -304,57 +328,74 @@ __global__ void __launch_bounds__(1024)
     if (threadIdx.x == 0) *total_out = carry;
 }
 
+// Scatter: one block per kSegBlock particles (the unit segment_count_kernel counted), walked in 16 sub-tiles of 256
+// with a running offset; inside a sub-tile the sticks are ranked with warp ballots.
 template <typename T>
 __global__ void __launch_bounds__(kStreamThreads)
     segment_write_kernel(Planes<T> P, Geom g, int cloth, const unsigned int* __restrict__ block_offsets,
                          float4* __restrict__ xyxy, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
                          unsigned long long cap) {
-    __shared__ unsigned int warp_base[kStreamThreads / 32];
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = (long long)g.own_rows * g.nx;
-    const long long base = (long long)cloth * g.cloth_stride;
-    bool v = false, h = false;
-    int ly = 0, cx = 0;
-    if (i < n) {
-        ly = (int)(i / g.nx);
-        cx = (int)(i % g.nx);
-        tail_sticks(P, g, base, ly, cx, v, h);
-    }
-    // warp-ballot ranking: within a warp, lane l's sticks come after all sticks of lanes < l
-    const uint32_t bv = __ballot_sync(0xffffffffu, v), bh = __ballot_sync(0xffffffffu, h);
+    __shared__ unsigned int warp_base[kStreamThreads / 32 + 1];
+    const long long n = (long long)g.own_rows * g.pitch;
+    const long long base = (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t below = (1u << lane) - 1u;
-    const unsigned int rank = __popc(bv & below) + __popc(bh & below);
-    const unsigned int wtot = __popc(bv) + __popc(bh);
-    if (lane == 0) warp_base[w] = wtot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int run = 0;
-        for (int k = 0; k < kStreamThreads / 32; k++) {
-            const unsigned int t = warp_base[k];
-            warp_base[k] = run;
-            run += t;
+    unsigned long long run = block_offsets[blockIdx.x];
+#pragma unroll 1
+    for (int sub = 0; sub < kSegPerThread; ++sub) {
+        const long long i = (long long)blockIdx.x * kSegBlock + sub * kStreamThreads + threadIdx.x;
+        if ((long long)blockIdx.x * kSegBlock + sub * kStreamThreads >= n) break;  // block-uniform
+        bool v = false, h = false;
+        int ly = 0, cx = 0;
+        uint32_t f = 0, fu = 0, fw = 0;
+        if (i < n) {
+            ly = (int)(i / g.pitch);
+            cx = (int)(i - (long long)ly * g.pitch);
+            f = P.fl[base + i];
+            if (f & CLOTHGPU_FLAG_ACTIVE) {
+                if (g.own_row0 + ly > g.held_row0) fu = P.fl[base + i - g.pitch];
+                if (cx > 0) fw = P.fl[base + i - 1];
+                v = (fu & CLOTHGPU_FLAG_ALIVE_V) && (fu & CLOTHGPU_FLAG_ACTIVE);
+                h = (fw & CLOTHGPU_FLAG_ALIVE_H) && (fw & CLOTHGPU_FLAG_ACTIVE);
+            }
         }
-    }
-    __syncthreads();
-    unsigned long long o = (unsigned long long)block_offsets[blockIdx.x] + warp_base[w] + rank;
-    if (!(v || h)) return;
-    const long long at = base + (long long)(g.own_row0 - g.held_row0 + ly) * g.pitch + cx;
-    const float x2 = (float)P.x[at], y2 = (float)P.y[at];  // cloth.go:110-111: float32(c.p2.x)
-    const bool hl2 = (P.fl[at] & CLOTHGPU_FLAG_HIGHLIGHT) != 0;
-    const unsigned int tail_i = (unsigned int)((long long)ly * g.nx + cx);
-    if (v) {
-        if (o < cap) {
-            xyxy[o] = make_float4((float)P.x[at - g.pitch], (float)P.y[at - g.pitch], x2, y2);
-            hl[o] = hl2 && (P.fl[at - g.pitch] & CLOTHGPU_FLAG_HIGHLIGHT);  // cloth.go:127-128
-            if (idx) idx[o] = make_uint2(tail_i - g.nx, tail_i);
+        // warp-ballot ranking: within a warp, lane l's sticks come after all sticks of lanes < l
+        const uint32_t bv = __ballot_sync(0xffffffffu, v), bh = __ballot_sync(0xffffffffu, h);
+        const unsigned int rank = __popc(bv & below) + __popc(bh & below);
+        if (lane == 0) warp_base[w] = __popc(bv) + __popc(bh);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int acc = 0;
+            for (int k = 0; k < kStreamThreads / 32; k++) {
+                const unsigned int t = warp_base[k];
+                warp_base[k] = acc;
+                acc += t;
+            }
+            warp_base[kStreamThreads / 32] = acc;
         }
-        o++;
-    }
-    if (h && o < cap) {
-        xyxy[o] = make_float4((float)P.x[at - 1], (float)P.y[at - 1], x2, y2);
-        hl[o] = hl2 && (P.fl[at - 1] & CLOTHGPU_FLAG_HIGHLIGHT);
-        if (idx) idx[o] = make_uint2(tail_i - 1, tail_i);
+        __syncthreads();
+        unsigned long long o = run + warp_base[w] + rank;
+        run += warp_base[kStreamThreads / 32];
+        if (v || h) {
+            const long long at = base + i;
+            const float x2 = (float)P.x[at], y2 = (float)P.y[at];  // cloth.go:110-111: float32(c.p2.x)
+            const bool hl2 = (f & CLOTHGPU_FLAG_HIGHLIGHT) != 0;
+            const unsigned int tail_i = (unsigned int)((long long)ly * g.nx + cx);
+            if (v) {
+                if (o < cap) {
+                    xyxy[o] = make_float4((float)P.x[at - g.pitch], (float)P.y[at - g.pitch], x2, y2);
+                    hl[o] = hl2 && (fu & CLOTHGPU_FLAG_HIGHLIGHT);  // cloth.go:127-128
+                    if (idx) idx[o] = make_uint2(tail_i - g.nx, tail_i);
+                }
+                o++;
+            }
+            if (h && o < cap) {
+                xyxy[o] = make_float4((float)P.x[at - 1], (float)P.y[at - 1], x2, y2);
+                hl[o] = hl2 && (fw & CLOTHGPU_FLAG_HIGHLIGHT);
+                if (idx) idx[o] = make_uint2(tail_i - 1, tail_i);
+            }
+        }
+        __syncthreads();  // warp_base is rewritten by the next sub-tile
     }
 }
 

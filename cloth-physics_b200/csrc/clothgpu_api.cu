@@ -865,11 +865,13 @@ int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* act
 
 namespace {
 // Live-stick compaction on the handle's stream: per-block counts, exclusive scan, ballot-ranked scatter into c->seg_out.
-int compact_enqueue(clothgpu* c, int32_t cloth, size_t* max_sticks_out) {
+int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, size_t* max_sticks_out) {
     if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
     const Geom& g = c->g;
     const long long n = (long long)g.nx * g.own_rows;
-    const unsigned blocks = (unsigned)((n + kStreamThreads - 1) / kStreamThreads);
+    const long long padded = (long long)g.pitch * g.own_rows;
+    const unsigned blocks = (unsigned)((padded + kSegBlock - 1) / kSegBlock);                         // scatter blocks
+    const unsigned count_blocks = blocks;  // 256 threads x 16 flag bytes = the particles of one scatter block
     if (c->seg_counts_cap < blocks) {
         cudaFree(c->seg_counts);
         c->seg_counts = nullptr;
@@ -890,9 +892,10 @@ int compact_enqueue(clothgpu* c, int32_t cloth, size_t* max_sticks_out) {
     auto run = [&](auto tag) {
         using T = decltype(tag);
         Planes<T> P = planes<T>(c, c->cur_pos, c->cur_prev);
-        segment_count_kernel<T><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
+        segment_count_kernel<T><<<count_blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
         segment_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_counts, (int)blocks, c->seg_total);
-        segment_write_kernel<T><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy, d_hl, d_idx, max_sticks);
+        segment_write_kernel<T><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy, d_hl,
+                                                                           with_idx ? d_idx : nullptr, max_sticks);
     };
     if (c->precision == CLOTHGPU_F32)
         run(float{});
@@ -907,7 +910,7 @@ int compact_enqueue(clothgpu* c, int32_t cloth, size_t* max_sticks_out) {
 
 int clothgpu_compact_segments(clothgpu* c, int32_t cloth) {
     if (int rc = check_handle(c)) return rc;
-    return compact_enqueue(c, cloth, nullptr);
+    return compact_enqueue(c, cloth, false, nullptr);
 }
 
 int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
@@ -915,7 +918,7 @@ int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t*
     if (int rc = check_handle(c)) return rc;
     if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
     size_t max_sticks = 0;
-    if (int rc = compact_enqueue(c, cloth, &max_sticks)) return rc;
+    if (int rc = compact_enqueue(c, cloth, sticks_idx != nullptr, &max_sticks)) return rc;
     float4* d_xyxy = (float4*)c->seg_out;
     uint2* d_idx = (uint2*)(d_xyxy + max_sticks);
     uint8_t* d_hl = (uint8_t*)(d_idx + max_sticks);
