@@ -18,7 +18,8 @@
 // joins).  Column halo: lane 0's even column misses its H-odd stick to the left and lane 31's odd column the one to
 // the right, so windows advance by 60 columns and lanes 0 / 31 are recomputed by the neighbouring warp (except at the
 // cloth's edge, where those sticks do not exist).  Row halo: a chunk reads two rows above and below its owned rows.
-// The next trip's ten loads are issued before the current trip's arithmetic (register double buffering).
+// Loads run two trips ahead of the arithmetic: every lane owns a small ring of shared-memory slots that cp.async fills
+// (a lane only reads back what it copied itself, so this needs no barrier and no registers for the data in flight).
 #pragma once
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
@@ -26,6 +27,12 @@
 
 namespace clothgpu_impl {
 
+#ifndef S1_MIN_CTAS
+#define S1_MIN_CTAS 4
+#endif
+#ifndef S1_RING_CTAS
+#define S1_RING_CTAS 5
+#endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
 constexpr int kS1WindowStep = 60;     // columns a window advances by (30 owned pairs + 1 halo pair per side)
 
@@ -36,14 +43,33 @@ struct Stream1Plan {
     long long tasks; // windows * chunks * ensemble
 };
 
+// Asynchronous global -> shared copy of one lane's 16 (8 in F32) bytes; pred == false zero-fills instead of reading.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_lane(void* smem, const void* gmem, bool pred) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = pred ? BYTES : 0;
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <typename T>
 struct RowRaw {  // one row of a lane's column pair, as loaded
     typename Vec2<T>::type x, y, px, py;
     uint32_t fl;  // low byte = even column, next byte = odd column
 };
 
-template <typename T, bool PER_CLOTH, bool DRAG>
-__global__ void __launch_bounds__(kS1Threads, 4)
+// RING == 0: the next trip's loads wait in registers.  RING >= 2: every lane owns RING slots of 8 x 16 B in shared memory
+// that cp.async fills RING trips ahead (a lane only ever reads back what it copied itself, so no barrier is involved):
+// more loads in flight, 34 fewer live registers.
+template <typename T, bool PER_CLOTH, bool DRAG, int RING>
+__global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     stream1_frame_kernel(Planes<T> in, Planes<T> out, Geom g, Stream1Plan pl, const FrameU<T> u0,
                          const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr, const PeerOut<T> peer_up,
                          const PeerOut<T> peer_dn) {
@@ -138,13 +164,65 @@ __global__ void __launch_bounds__(kS1Threads, 4)
     cE.x = cE.y = cO.x = cO.y = T(0);
     uint32_t cfe = 0, cfo = 0;
 
-    RowRaw<T> nxt0 = load_row(rs), nxt1 = load_row(rs + 1);
+    // ---- prefetch machinery -------------------------------------------------------------------------------------
+    extern __shared__ __align__(16) unsigned char s1_smem[];
+    // slot (stage, q, plane) of this lane: 32 lanes x sizeof(V2) contiguous, conflict-free
+    auto slot = [&](int stage, int q, int plane) -> V2* {
+        return reinterpret_cast<V2*>(s1_smem) + ((((threadIdx.x >> 5) * (RING ? RING : 1) + stage) * 8 + q * 4 + plane) * 32 + lane);
+    };
+    auto issue_trip = [&](int r, int stage) {  // rows r, r+1 -> stage (RING > 0 only)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int gy = r + q;
+            const bool ok = gy < re && ex_e;
+            const long long at = ok ? cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce : 0;
+            cp_async_lane<sizeof(V2)>(slot(stage, q, 0), in.x + at, ok);
+            cp_async_lane<sizeof(V2)>(slot(stage, q, 1), in.y + at, ok);
+            cp_async_lane<sizeof(V2)>(slot(stage, q, 2), in.px + at, ok);
+            cp_async_lane<sizeof(V2)>(slot(stage, q, 3), in.py + at, ok);
+        }
+        cp_async_commit();
+    };
+    auto load_flags = [&](int gy) -> uint32_t {
+        uint32_t f = 0;
+        if (gy < re && ex_e) {
+            f = *reinterpret_cast<const unsigned short*>(in.fl + cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce);
+            if (!ex_o) f &= 0xffu;
+        }
+        return f;
+    };
+
+    RowRaw<T> nxt0, nxt1;
+    uint32_t fq[RING ? 2 * RING : 1];  // flags of the trips in flight (RING > 0)
+    if (RING == 0) {
+        nxt0 = load_row(rs), nxt1 = load_row(rs + 1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RING; ++k) {
+            issue_trip(rs + 2 * k, k);
+            fq[2 * k] = load_flags(rs + 2 * k), fq[2 * k + 1] = load_flags(rs + 2 * k + 1);
+        }
+    }
+    int stage = 0;
 #pragma unroll 1
     for (int r = rs; r < re; r += 2) {
-        // (a ping-pong of two register sets instead of these copies measured slower: twice the code, worse schedule)
-        const RowRaw<T> raw0 = nxt0, raw1 = nxt1;
-        nxt0 = load_row(r + 2);  // in flight during this trip's arithmetic (rows >= re load nothing)
-        nxt1 = load_row(r + 3);
+        RowRaw<T> raw0, raw1;
+        if (RING == 0) {
+            // (a ping-pong of two register sets instead of these copies measured slower: twice the code, worse schedule)
+            raw0 = nxt0, raw1 = nxt1;
+            nxt0 = load_row(r + 2);  // in flight during this trip's arithmetic (rows >= re load nothing)
+            nxt1 = load_row(r + 3);
+        } else {
+            cp_async_wait<RING - 1>();  // the oldest group (this trip) has landed
+            raw0.x = *slot(stage, 0, 0), raw0.y = *slot(stage, 0, 1), raw0.px = *slot(stage, 0, 2), raw0.py = *slot(stage, 0, 3);
+            raw1.x = *slot(stage, 1, 0), raw1.y = *slot(stage, 1, 1), raw1.px = *slot(stage, 1, 2), raw1.py = *slot(stage, 1, 3);
+            raw0.fl = fq[0], raw1.fl = fq[1];
+#pragma unroll
+            for (int k = 0; k + 1 < RING; ++k) fq[2 * k] = fq[2 * k + 2], fq[2 * k + 1] = fq[2 * k + 3];
+            issue_trip(r + 2 * RING, stage);  // refill the slots just read (always commits, so group counting stays uniform)
+            fq[2 * RING - 2] = load_flags(r + 2 * RING), fq[2 * RING - 1] = load_flags(r + 2 * RING + 1);
+            stage = stage + 1 == RING ? 0 : stage + 1;
+        }
         V2 E[2], O[2];
         uint32_t fe[2], fo[2];
 #pragma unroll

@@ -83,6 +83,8 @@ struct clothgpu {
     int sweeps_per_launch = kMaxSweepsPerLaunch;
     int k1_stream = 1;       // 1: frames with one sweep take the register-streaming kernel (cloth_stream1.cuh)
     int s1_chunk_rows = 0;   // 0: chosen per launch
+    int s1_ring = 2;         // shared-memory prefetch ring depth of stream1_frame_kernel (0: register prefetch)
+    int s1_warps_per_sm = 4 * S1_RING_CTAS;  // resident warps of stream1_frame_kernel per SM (its launch bounds)
     // All state planes and the strip epoch slots live in ONE device allocation, so a neighbouring strip (another
     // process, another GPU) maps everything with a single cudaIpcMemHandle.
     void* slab = nullptr;
@@ -315,9 +317,9 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
     Stream1Plan pl{};
     pl.windows = g.nx <= 64 ? 1 : (g.nx - 64 + kS1WindowStep - 1) / kS1WindowStep + 1;
     // Row chunks.  Warps are independent and equally loaded, so the launch runs in "waves" of `slots` resident warps
-    // (16 per SM at 128 registers): long chunks amortise the 4 halo rows, but the task count should be just under a
+    // (20 per SM with the shared-memory prefetch ring): long chunks amortise the 4 halo rows, but the task count should be just under a
     // whole number of waves.  With many waves the last, partial one no longer matters and 128-row chunks are used.
-    const long long slots = (long long)c->sm_count * 16;
+    const long long slots = (long long)c->sm_count * c->s1_warps_per_sm;
     const long long per_chunk = (long long)pl.windows * g.ensemble;  // tasks added by one more chunk
     int R = c->s1_chunk_rows;
     if (R < 2) {
@@ -340,12 +342,26 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
     if (int rc = strip_begin_op(c)) return rc;
     const unsigned blocks = (unsigned)((pl.tasks + kS1Threads / 32 - 1) / (kS1Threads / 32));
     const bool pc = per_cloth != nullptr;
-    if (pc)
-        stream1_frame_kernel<T, true, true><<<blocks, kS1Threads, 0, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
-    else if (u.buttons & CLOTHGPU_MOUSE_DRAGGING)
-        stream1_frame_kernel<T, false, true><<<blocks, kS1Threads, 0, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
-    else
-        stream1_frame_kernel<T, false, false><<<blocks, kS1Threads, 0, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+    const bool drag = pc || (u.buttons & CLOTHGPU_MOUSE_DRAGGING);
+    auto go = [&](auto kernel, size_t smem) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<blocks, kS1Threads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+        return cudaSuccess;
+    };
+    auto pick = [&](auto ring) -> cudaError_t {
+        constexpr int RING = decltype(ring)::value;
+        const size_t smem = (size_t)RING * kS1Threads * 8 * 2 * sizeof(T);
+        if (pc) return go(stream1_frame_kernel<T, true, true, RING>, smem);
+        return drag ? go(stream1_frame_kernel<T, false, true, RING>, smem) : go(stream1_frame_kernel<T, false, false, RING>, smem);
+    };
+    switch (c->s1_ring) {
+        case 2: CU_TRY(pick(std::integral_constant<int, 2>{})); break;
+        case 3: CU_TRY(pick(std::integral_constant<int, 3>{})); break;
+        default: CU_TRY(pick(std::integral_constant<int, 0>{})); break;
+    }
     CU_TRY(cudaGetLastError());
     c->launches++;
     c->cur_pos = nxt;
@@ -608,6 +624,11 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     if (const char* s = getenv("CLOTHGPU_FUSED_VARIANT")) c->fused_variant = atoi(s);
     if (const char* s = getenv("CLOTHGPU_K1_STREAM")) c->k1_stream = atoi(s);
     if (const char* s = getenv("CLOTHGPU_S1_ROWS")) c->s1_chunk_rows = atoi(s) & ~1;
+    if (const char* s = getenv("CLOTHGPU_S1_RING")) {
+        c->s1_ring = atoi(s);
+        c->s1_warps_per_sm = c->s1_ring == 2 ? 4 * S1_RING_CTAS : 4 * S1_MIN_CTAS;  // (3 stages: 48 KB per CTA, 4 CTAs fit)
+    }
+    if (const char* s = getenv("CLOTHGPU_S1_WARPS")) c->s1_warps_per_sm = std::max(1, atoi(s));
     if (const char* s = getenv("CLOTHGPU_SWEEPS_PER_LAUNCH")) {
         const int v = atoi(s);
         if (v >= 1 && v <= kMaxSweepsPerLaunch) c->sweeps_per_launch = v;
