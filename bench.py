@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--impl", default="clothgpu", choices=["clothgpu", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream", "streaming"],
+    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream", "wave", "streaming"],
                     help="auto = what clothgpu_step picks itself: the row-streaming kernel for one-sweep frames, the tile kernel otherwise")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -261,7 +261,7 @@ def main():
     else:
         cloth = clothgpu.Cloth(make_desc(_abi, wl, local, precision))
     cloth.set_schedule({"auto": _abi.SCHED_AUTO, "fused": _abi.SCHED_FUSED, "rowstream": _abi.SCHED_ROWSTREAM,
-                        "streaming": _abi.SCHED_STREAMING}[args.schedule])
+                        "wave": _abi.SCHED_WAVE, "streaming": _abi.SCHED_STREAMING}[args.schedule])
     stream = torch.cuda.Stream()
     cloth.set_stream(stream.cuda_stream)
     frame = make_frame(_abi, wl)

@@ -1,0 +1,489 @@
+// cloth_wave.cuh — the wavefront schedule for frames with several sweeps: ONE launch per frame, rows streamed through
+// a ring of shared memory, the K sweeps pipelined along the row direction.
+//
+// The tile kernel (cloth_fused.cuh) loads a 128 x 100 tile, runs K sweeps on it and stores it: its arithmetic is 1.5x
+// redundant for K = 8 (a 16-wide stale rim on all four sides) and its load / store phases do not overlap the sweeps.
+// Here a CTA owns a band of 256 columns and a chunk of rows, and streams the rows downwards:
+//
+//     entry    rows (2q, 2q+1) arrive (cp.async staging ring, three pairs ahead), particle loop (cloth.go:92-94),
+//              H-even of sweep 0, then they join the ring of 4K+4 rows
+//     stage j  (sweep j, j = 0..K-1) works 2 row pairs behind stage j-1:
+//                A_j(p) = H-odd(j) + V-even(j)    on rows (2p,   2p+1),   at step s = p + 2j
+//                B_j(p) = V-odd(j) + H-even(j+1)  on rows (2p+1, 2p+2),   at step s = p + 2j + 1
+//              (the same 2x2-blocks-in-registers passes as the tile kernel); B_{K-1} writes its rows back to HBM
+//
+// A step = { all A_j, entry of the next pair } barrier { all B_j } barrier, so every barrier interval carries the work
+// of all K sweeps.  Dependencies: B_j(p) needs A_j(p) (previous step) and A_j(p+1) (same step, before the barrier);
+// A_{j+1}(p) needs B_j(p-1) and B_j(p) (both in earlier steps) — hence the lag of two pairs per sweep.
+// Rows are never recomputed (only the 2K halo rows above and below a chunk, trapezoid-wise as in the tile kernel), the
+// column halo is 2K of 256 instead of 2K of 128, and HBM traffic is spread evenly over the whole launch.
+//
+// Threads: 16 worker warps (8 groups of 64 column pairs; a phase has 2K half-band items, group g takes items g, g+8)
+// + 4 entry warps (one column pair per thread).  Validity of the stale rim is decided per item (rows, warp-uniform) and per thread and stage
+// (columns), exactly as in the tile kernel.  Local rows are offset by 2 so that pair 0 is an all-zero dummy pair:
+// B_j(0) = rows (1, 2) then gives the first real row its H-even pass without a special case.
+#pragma once
+#include <type_traits>
+
+#include "cloth_fused.cuh"
+#include "cloth_stream1.cuh"
+
+namespace clothgpu_impl {
+
+constexpr int kWaveTW = 256, kWaveHW = 128;
+constexpr int kWaveWorkers = 512, kWaveEntry = 128, kWaveThreads = kWaveWorkers + kWaveEntry;
+constexpr int kWaveGroups = kWaveWorkers / 64;  // worker groups of 64 column pairs
+constexpr int kWaveDepth = 3;                   // row pairs in flight in the staging ring
+#ifndef WAVE_BOTH
+#define WAVE_BOTH 0
+#endif
+constexpr bool kWaveBoth = WAVE_BOTH != 0;      // both items of a thread at once (4 sticks in flight) or one after the other
+
+struct WavePlan {
+    int K, h, RB;     // sweeps, halo = 2K, ring rows = 4K + 4
+    int bands;        // column bands per cloth
+    int first_w, mid_w;
+    int chunk_rows, chunks;
+};
+
+template <typename T>
+__host__ __device__ constexpr size_t wave_smem_bytes(int RB) {
+    return (size_t)RB * kWaveHW * 2 * 2 * sizeof(T)                      // xyE, xyO
+           + (size_t)RB * kWaveTW                                        // fl8
+           + (size_t)(RB / 2) * kWaveHW * 2 * sizeof(uint16_t)           // stA, stB
+           + (size_t)kWaveDepth * 2 * 4 * kWaveHW * 2 * sizeof(T);       // staging: pairs x rows x planes x 128 column pairs
+}
+
+template <typename T, bool PER_CLOTH, bool DRAG>
+__global__ void __launch_bounds__(kWaveThreads, 1)
+    wave_frame_kernel(Planes<T> in, Planes<T> out, Geom g, WavePlan pl, const FrameU<T> u0,
+                      const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr, const PeerOut<T> peer_up,
+                      const PeerOut<T> peer_dn) {
+    using V2 = typename Vec2<T>::type;
+    constexpr int TW = kWaveTW, HW = kWaveHW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int RB = pl.RB, HP = RB >> 1, K = pl.K, h = pl.h;
+    V2* xyE = reinterpret_cast<V2*>(smem_raw);
+    V2* xyO = xyE + RB * HW;
+    uint8_t* fl8 = reinterpret_cast<uint8_t*>(xyO + RB * HW);
+    uint16_t* stA = reinterpret_cast<uint16_t*>(fl8 + (size_t)RB * TW);
+    uint16_t* stB = stA + HP * HW;
+    V2* stage = reinterpret_cast<V2*>(stB + HP * HW);  // [kWaveDepth][2][4][HW]
+
+    const int e = blockIdx.z;
+    const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
+    const bool dragging = DRAG && (u.buttons & CLOTHGPU_MOUSE_DRAGGING) != 0;
+    const int tid = threadIdx.x;
+
+    // ---- band (columns) and chunk (rows) of this CTA ------------------------------------------------------------
+    const int bx = blockIdx.x;
+    const int ix0 = bx == 0 ? 0 : pl.first_w + (bx - 1) * pl.mid_w;  // interior columns [ix0, ix1)
+    const int ix1 = min(g.nx, bx == 0 ? pl.first_w : ix0 + pl.mid_w);
+    const int ox = bx == 0 ? 0 : ix0 - h;  // band origin column
+    const int cols = min(TW, g.nx - ox);
+    const bool halo_left = ox > 0, halo_right = ox + TW < g.nx;
+    const int lx0 = ix0 - ox, lx1 = ix1 - ox;
+    const int held_end = g.held_row0 + g.held_rows, own_end = g.own_row0 + g.own_rows;
+    const int ra = g.own_row0 + blockIdx.y * pl.chunk_rows, rb = min(ra + pl.chunk_rows, own_end);  // owned rows
+    const int y0 = max(g.held_row0, ra - h), y1 = min(held_end, rb + h);                            // rows streamed
+    const bool halo_top = y0 > g.held_row0, halo_bottom = y1 < held_end;
+    const int n_lr = y1 - y0 + 2;  // local rows: 0, 1 = dummy zero pair, real rows [2, n_lr)
+    const int ly0 = ra - y0 + 2, ly1 = rb - y0 + 2;  // owned rows, local
+    const long long cloth_base = (long long)e * g.cloth_stride;
+    auto row_off = [&](int lr) -> long long {  // element offset of local row lr, column ox
+        return cloth_base + (long long)(y0 + lr - 2 - g.held_row0) * g.pitch + ox;
+    };
+    auto slot = [&](int lr) -> int { return lr % RB; };
+
+    unsigned int acc_live = 0, acc_torn = 0, acc_torn_post = 0, acc_extra = 0;
+    auto owned = [&](int lr, int c) -> bool { return lr >= ly0 && lr < ly1 && c >= lx0 && c < lx1; };
+    // a torn stick (after the block states were derived): clear the alive bit of its head's flag byte
+    auto tear = [&](int lr, int c, uint32_t alive_bit, int sweep) {
+        fl8[slot(lr) * TW + c] &= (uint8_t)~alive_bit;
+        if (owned(lr, c)) acc_torn += 1, acc_torn_post += 1, acc_extra += (unsigned)(sweep + 1);
+    };
+
+    // ---- prologue: the dummy pair -----------------------------------------------------------------------------------
+    for (int i = tid; i < 2 * HW; i += kWaveThreads) {
+        V2 z;
+        z.x = z.y = T(0);
+        xyE[i] = z, xyO[i] = z;  // rows 0 and 1 are slots 0 and 1
+    }
+    for (int i = tid; i < 2 * TW; i += kWaveThreads) fl8[i] = 0;
+    // (stA/stB of pair 0 are never read: A_j(0) is skipped, B_j(0) of stage 0 derives its own)
+
+    const int last_pair = (n_lr + 1) >> 1;  // entry also delivers one all-zero pair past the end (row n_lr may be a B tail)
+    const int n_steps = last_pair + 2 * K + 1;
+
+    if (tid >= kWaveWorkers) {
+        // =============================== entry warps ===============================================================
+        const int et = tid - kWaveWorkers;  // 0..127: the column pair this thread delivers, both rows of a pair
+        const int c = 2 * et;
+        auto st_slot = [&](int q, int row, int plane) -> V2* {
+            return stage + ((((q % kWaveDepth) * 2 + row) * 4 + plane) * HW + et);
+        };
+        auto issue_pair = [&](int q) {  // local rows 2q, 2q+1 -> staging
+#pragma unroll
+            for (int row = 0; row < 2; ++row) {
+                const int lr = 2 * q + row;
+                const bool ok = q >= 1 && lr < n_lr && c < cols;
+                const long long at = ok ? row_off(lr) + c : 0;
+                cp_async_lane<sizeof(V2)>(st_slot(q, row, 0), in.x + at, ok);
+                cp_async_lane<sizeof(V2)>(st_slot(q, row, 1), in.y + at, ok);
+                cp_async_lane<sizeof(V2)>(st_slot(q, row, 2), in.px + at, ok);
+                cp_async_lane<sizeof(V2)>(st_slot(q, row, 3), in.py + at, ok);
+            }
+            cp_async_commit();
+        };
+        auto load_flags = [&](int q, int row) -> uint32_t {
+            const int lr = 2 * q + row;
+            uint32_t f = 0;
+            if (q >= 1 && lr < n_lr && c < cols) {
+                f = *reinterpret_cast<const unsigned short*>(in.fl + row_off(lr) + c);
+                if (c + 1 >= cols) f &= 0xffu;  // column nx (row padding) does not exist
+            }
+            return f;
+        };
+#pragma unroll
+        for (int q = 1; q <= kWaveDepth; ++q) issue_pair(q);
+        uint32_t fnext[2] = {load_flags(1, 0), load_flags(1, 1)};
+        __syncthreads();  // (matches the workers' prologue barrier)
+        int eslot = 2;  // ring slot of local row 2q (q = 1 at the first step)
+#pragma unroll 1
+        for (int s = 0; s < n_steps; ++s) {
+            const int q = s + 1;  // the pair delivered during this step
+            if (q <= last_pair) {
+                cp_async_wait<kWaveDepth - 1>();
+                const uint32_t fcur[2] = {fnext[0], fnext[1]};
+                fnext[0] = load_flags(q + 1, 0), fnext[1] = load_flags(q + 1, 1);
+                V2 p0[2], p1[2];
+                uint32_t f0[2], f1[2];
+#pragma unroll
+                for (int row = 0; row < 2; ++row) {
+                    const int lr = 2 * q + row;
+                    const V2 vx = *st_slot(q, row, 0), vy = *st_slot(q, row, 1);
+                    const V2 vpx = *st_slot(q, row, 2), vpy = *st_slot(q, row, 3);
+                    p0[row].x = vx.x, p1[row].x = vx.y, p0[row].y = vy.x, p1[row].y = vy.y;
+                    f0[row] = fcur[row] & 0xffu, f1[row] = fcur[row] >> 8;
+                    if (lr < n_lr && c < cols) {
+                        T px0 = vpx.x, px1 = vpx.y, py0 = vpy.x, py1 = vpy.y;
+                        particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], u);
+                        if (c + 1 < cols) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
+                        if (owned(lr, c)) {  // the owner of a particle writes its previous position
+                            const long long at = row_off(lr) + c;
+                            const int gy = y0 + lr - 2, gx = ox + c;
+                            V2 ox2, oy2;
+                            ox2.x = px0, ox2.y = px1, oy2.x = py0, oy2.y = py1;
+                            *reinterpret_cast<V2*>(out.px + at) = ox2;
+                            *reinterpret_cast<V2*>(out.py + at) = oy2;
+                            if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {
+                                const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + gx;
+                                *reinterpret_cast<V2*>(peer_up.px + pat) = ox2;
+                                *reinterpret_cast<V2*>(peer_up.py + pat) = oy2;
+                            }
+                            if (gy >= peer_dn.row_lo && gy < peer_dn.row_hi) {
+                                const long long pat = (long long)e * peer_dn.cloth_stride + (long long)(gy - peer_dn.held_row0) * g.pitch + gx;
+                                *reinterpret_cast<V2*>(peer_dn.px + pat) = ox2;
+                                *reinterpret_cast<V2*>(peer_dn.py + pat) = oy2;
+                            }
+                        }
+                    }
+                }
+                issue_pair(q + kWaveDepth);  // refill the staging slots just read (always commits: uniform group counting)
+                {  // H-even of sweep 0: the two rows of this column pair
+                    V2* hh[2] = {&p0[0], &p0[1]};
+                    V2* tt[2] = {&p1[0], &p1[1]};
+                    uint32_t live = 0, pins = 0;
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        if ((f0[w] & CLOTHGPU_FLAG_ALIVE_H) && (f0[w] & f1[w] & CLOTHGPU_FLAG_ACTIVE)) live |= 1u << w;  // cloth.go:97
+                        pins |= ((f0[w] & CLOTHGPU_FLAG_PIN) | ((f1[w] & CLOTHGPU_FLAG_PIN) << 1)) << (2 * w);
+                    }
+                    bool touched = false;
+                    const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, dragging, touched);
+                    if (DRAG && tore) {
+#pragma unroll
+                        for (int w = 0; w < 2; ++w)
+                            if (tore & (1u << w)) {
+                                f0[w] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_H;
+                                if (owned(2 * q + w, c)) acc_torn += 1, acc_extra += 1;
+                            }
+                    }
+                }
+#pragma unroll
+                for (int row = 0; row < 2; ++row) {
+                    const int sl = eslot + row;
+                    xyE[sl * HW + et] = p0[row];
+                    xyO[sl * HW + et] = p1[row];
+                    *reinterpret_cast<uint16_t*>(fl8 + sl * TW + c) = (uint16_t)(f0[row] | (f1[row] << 8));
+                }
+            }
+            __syncthreads();  // end of phase alpha
+            __syncthreads();  // end of phase beta
+            eslot = eslot + 2 == RB ? 0 : eslot + 2;
+        }
+    } else {
+        // =============================== worker warps ==============================================================
+        // A thread works for the same (at most two) sweep stages and the same column pair during the whole launch, so
+        // everything that depends on them is computed once: column masks, row ranges, and the ring slots advance by two
+        // rows per step.
+        const int grp = tid >> 6, k64 = tid & 63;
+        const int k = (grp & 1) * 64 + k64, kr = (k + 1) & (HW - 1);
+        const int cl = 2 * k + 1, cr = 2 * kr, ce = 2 * k, co = ce + 1;
+        constexpr int kItems = 2;  // ceil(2 * 8 / kWaveGroups)
+        int jj[kItems], e2[kItems], rloA[kItems], rhiA[kItems], rloB[kItems], rhiB[kItems];
+        uint32_t maskA[kItems], maskB[kItems];
+        bool on[kItems];
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int j = (grp >> 1) + i * (kWaveGroups / 2);
+            jj[i] = j;
+            on[i] = j < K;
+            e2[i] = j == 0 ? 0 : RB - 4 * j;  // slot of row 2p for p = -2j (step 0); 4j < RB
+            const int c0 = halo_left ? 2 * j : 0, c1 = halo_right ? TW - 2 * j : cols;              // sweep j's columns
+            const int d0 = halo_left ? 2 * j + 2 : 0, d1 = halo_right ? TW - 2 * j - 2 : cols;      // sweep j+1's columns
+            maskA[i] = (cl >= c0 && cl + 1 < c1) ? 0xfu : kStSecond;                                // H-odd needs both columns
+            maskB[i] = (j + 1 < K && ce >= d0 && co < d1) ? 0xfu : kStFirst;                        // H-even(j+1) likewise
+            rloA[i] = halo_top ? 2 + 2 * j : 2, rhiA[i] = halo_bottom ? n_lr - 2 * j : n_lr;
+            rloB[i] = halo_top ? 2 + 2 * j : 0, rhiB[i] = halo_bottom ? n_lr - 2 * j : n_lr + 1;
+        }
+        __syncthreads();  // prologue: the dummy pair is in place
+        auto live_bit = [](uint32_t fh, uint32_t ft, uint32_t alive) -> uint32_t {
+            return ((fh & alive) && (fh & ft & CLOTHGPU_FLAG_ACTIVE)) ? 1u : 0u;  // cloth.go:97
+        };
+        auto pack = [&](uint32_t fa, uint32_t fb, uint32_t fc, uint32_t fd, uint32_t first_alive, uint32_t second_alive,
+                        bool first_ok) -> uint32_t {
+            uint32_t st = 0;
+            if (first_ok) st |= live_bit(fa, fb, first_alive) | (live_bit(fc, fd, first_alive) << 1);
+            st |= (live_bit(fa, fc, second_alive) << 2) | (live_bit(fb, fd, second_alive) << 3);
+            const uint32_t pa = fa & CLOTHGPU_FLAG_PIN, pb = fb & CLOTHGPU_FLAG_PIN, pc = fc & CLOTHGPU_FLAG_PIN,
+                           pd = fd & CLOTHGPU_FLAG_PIN;  // CLOTHGPU_FLAG_PIN == 1
+            st |= (pa << 4) | (pb << 5) | (pc << 6) | (pd << 7);
+            st |= (pa << 8) | (pc << 9) | (pb << 10) | (pd << 11);
+            return st;
+        };
+        // One phase for NI of this thread's items at once (2 * NI sticks in flight per pass: the relaxation of a stick is
+        // one long dependent binary64 chain, and with 4 worker warps per scheduler the pipe needs the extra chains).
+        auto phase_alpha = [&](auto ni, int i0, int s) {
+            constexpr int NI = decltype(ni)::value, NS = 2 * NI;
+            V2 pa[NI], pb[NI], pc[NI], pd[NI];
+            uint32_t st[NI];
+            int sa[NI], pp[NI], jn[NI];
+            uint32_t live1 = 0, live2 = 0, pins1 = 0, pins2 = 0;
+#pragma unroll
+            for (int n = 0; n < NI; ++n) {
+                const int i = i0 + n;
+                jn[n] = jj[i], pp[n] = s - 2 * jj[i], sa[n] = e2[i];  // slots of rows 2p, 2p+1 = sa, sa+1; state slot sa/2
+                const int sb = sa[n] + 1;
+                pa[n] = xyO[sa[n] * HW + k], pb[n] = xyE[sa[n] * HW + kr], pc[n] = xyO[sb * HW + k], pd[n] = xyE[sb * HW + kr];
+                if (jn[n] == 0) {  // derive the block state from the flag bytes (warp-uniform branch)
+                    const uint32_t fa = fl8[sa[n] * TW + cl], fb = fl8[sa[n] * TW + cr], fc = fl8[sb * TW + cl], fd = fl8[sb * TW + cr];
+                    st[n] = pack(fa, fb, fc, fd, CLOTHGPU_FLAG_ALIVE_H, CLOTHGPU_FLAG_ALIVE_V, k + 1 < HW);
+                    stA[(sa[n] >> 1) * HW + k] = (uint16_t)st[n];
+                    // sticks headed by an owned particle: a (H, V), c (H), b (V)
+                    const bool oa = owned(2 * pp[n], cl), oc = owned(2 * pp[n] + 1, cl), ob = owned(2 * pp[n], cr);
+                    acc_live += (oa ? (st[n] & 1u) + ((st[n] >> 2) & 1u) : 0u) + (oc ? (st[n] >> 1) & 1u : 0u) + (ob ? (st[n] >> 3) & 1u : 0u);
+                } else {
+                    st[n] = stA[(sa[n] >> 1) * HW + k];
+                }
+                const uint32_t sm = st[n] & maskA[i];
+                live1 |= (sm & 3u) << (2 * n), live2 |= ((sm >> 2) & 3u) << (2 * n);
+                pins1 |= ((st[n] >> 4) & 15u) << (4 * n), pins2 |= ((st[n] >> 8) & 15u) << (4 * n);
+            }
+            bool touched = false;
+            uint32_t tore1, tore2;
+            {  // H-odd: a->b and c->d
+                V2* hh[NS];
+                V2* tt[NS];
+#pragma unroll
+                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
+                tore1 = relax_n<T, DRAG, NS>(hh, tt, live1, pins1, u, dragging, touched);
+            }
+            {  // V-even: a->c and b->d
+                V2* hh[NS];
+                V2* tt[NS];
+#pragma unroll
+                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
+                tore2 = relax_n<T, DRAG, NS>(hh, tt, live2, pins2, u, dragging, touched);
+            }
+            if (DRAG && (tore1 | tore2)) {  // rare
+#pragma unroll
+                for (int n = 0; n < NI; ++n) {
+                    const uint32_t t1 = (tore1 >> (2 * n)) & 3u, t2 = (tore2 >> (2 * n)) & 3u;
+                    if (t1 | t2) {
+                        stA[(sa[n] >> 1) * HW + k] = (uint16_t)(st[n] & ~(t1 | (t2 << 2)));
+                        if (t1 & 1u) tear(2 * pp[n], cl, CLOTHGPU_FLAG_ALIVE_H, jn[n]);
+                        if (t1 & 2u) tear(2 * pp[n] + 1, cl, CLOTHGPU_FLAG_ALIVE_H, jn[n]);
+                        if (t2 & 1u) tear(2 * pp[n], cl, CLOTHGPU_FLAG_ALIVE_V, jn[n]);
+                        if (t2 & 2u) tear(2 * pp[n], cr, CLOTHGPU_FLAG_ALIVE_V, jn[n]);
+                    }
+                }
+            }
+            if (touched) {
+#pragma unroll
+                for (int n = 0; n < NI; ++n) {
+                    const int sb = sa[n] + 1;
+                    xyO[sa[n] * HW + k] = pa[n], xyE[sa[n] * HW + kr] = pb[n], xyO[sb * HW + k] = pc[n], xyE[sb * HW + kr] = pd[n];
+                }
+            }
+        };
+        auto phase_beta = [&](auto ni, int i0, int s) {
+            constexpr int NI = decltype(ni)::value, NS = 2 * NI;
+            V2 pa[NI], pb[NI], pc[NI], pd[NI];
+            uint32_t st[NI];
+            int sa[NI], sb[NI], pp[NI], jn[NI];
+            uint32_t live1 = 0, live2 = 0, pins1 = 0, pins2 = 0;
+            bool any_mid = false;  // some item still has an H-even pass to do (it is not the last sweep's)
+#pragma unroll
+            for (int n = 0; n < NI; ++n) {
+                const int i = i0 + n;
+                jn[n] = jj[i], pp[n] = s - 2 * jj[i] - 1;
+                const int s2p = e2[i] == 0 ? RB - 2 : e2[i] - 2;  // slot of row 2p (this pair is one behind A's)
+                sa[n] = s2p + 1, sb[n] = e2[i];
+                pa[n] = xyE[sa[n] * HW + k], pc[n] = xyO[sa[n] * HW + k], pb[n] = xyE[sb[n] * HW + k], pd[n] = xyO[sb[n] * HW + k];
+                if (jn[n] == 0) {
+                    const uint32_t fa2 = *reinterpret_cast<const uint16_t*>(fl8 + sa[n] * TW + ce);
+                    const uint32_t fb2 = *reinterpret_cast<const uint16_t*>(fl8 + sb[n] * TW + ce);
+                    st[n] = pack(fa2 & 0xffu, fb2 & 0xffu, fa2 >> 8, fb2 >> 8, CLOTHGPU_FLAG_ALIVE_V, CLOTHGPU_FLAG_ALIVE_H, true);
+                    stB[(s2p >> 1) * HW + k] = (uint16_t)st[n];
+                    // heads: a = (2p+1, ce) (V, H), c = (2p+1, co) (V), b = (2p+2, ce) (H)
+                    const bool oa = owned(2 * pp[n] + 1, ce), oc = owned(2 * pp[n] + 1, co), ob = owned(2 * pp[n] + 2, ce);
+                    acc_live += (oa ? (st[n] & 1u) + ((st[n] >> 2) & 1u) : 0u) + (oc ? (st[n] >> 1) & 1u : 0u) + (ob ? (st[n] >> 3) & 1u : 0u);
+                } else {
+                    st[n] = stB[(s2p >> 1) * HW + k];
+                }
+                const uint32_t sm = st[n] & maskB[i];  // (the last sweep's mask has no second-pass bits)
+                live1 |= (sm & 3u) << (2 * n), live2 |= ((sm >> 2) & 3u) << (2 * n);
+                pins1 |= ((st[n] >> 4) & 15u) << (4 * n), pins2 |= ((st[n] >> 8) & 15u) << (4 * n);
+                any_mid |= jn[n] + 1 < K;
+            }
+            bool touched = false;
+            uint32_t tore1, tore2 = 0;
+            {  // V-odd: a->b and c->d
+                V2* hh[NS];
+                V2* tt[NS];
+#pragma unroll
+                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
+                tore1 = relax_n<T, DRAG, NS>(hh, tt, live1, pins1, u, dragging, touched);
+            }
+            if (any_mid) {  // H-even of the next sweep: a->c and b->d (warp-uniform)
+                V2* hh[NS];
+                V2* tt[NS];
+#pragma unroll
+                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
+                tore2 = relax_n<T, DRAG, NS>(hh, tt, live2, pins2, u, dragging, touched);
+            }
+            if (DRAG && (tore1 | tore2)) {  // rare
+#pragma unroll
+                for (int n = 0; n < NI; ++n) {
+                    const uint32_t t1 = (tore1 >> (2 * n)) & 3u, t2 = (tore2 >> (2 * n)) & 3u;
+                    if (t1 | t2) {
+                        stB[((sa[n] - 1) >> 1) * HW + k] = (uint16_t)(st[n] & ~(t1 | (t2 << 2)));
+                        if (t1 & 1u) tear(2 * pp[n] + 1, ce, CLOTHGPU_FLAG_ALIVE_V, jn[n]);
+                        if (t1 & 2u) tear(2 * pp[n] + 1, co, CLOTHGPU_FLAG_ALIVE_V, jn[n]);
+                        if (t2 & 1u) tear(2 * pp[n] + 1, ce, CLOTHGPU_FLAG_ALIVE_H, jn[n] + 1);
+                        if (t2 & 2u) tear(2 * pp[n] + 2, ce, CLOTHGPU_FLAG_ALIVE_H, jn[n] + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < NI; ++n) {
+                if (jn[n] + 1 < K) {
+                    if (touched) xyE[sa[n] * HW + k] = pa[n], xyO[sa[n] * HW + k] = pc[n], xyE[sb[n] * HW + k] = pb[n], xyO[sb[n] * HW + k] = pd[n];
+                } else if (ce >= lx0 && ce < lx1) {
+                    // ---- the last colour pass is done: rows 2p+1 and 2p+2 leave through the registers --------------------------
+                    const uint32_t fa2 = *reinterpret_cast<const uint16_t*>(fl8 + sa[n] * TW + ce);  // (after possible tears of this pass)
+                    const uint32_t fb2 = *reinterpret_cast<const uint16_t*>(fl8 + sb[n] * TW + ce);
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int lr = 2 * pp[n] + 1 + w;
+                        if (lr >= ly0 && lr < ly1) {
+                            const V2 pe = w ? pb[n] : pa[n], po = w ? pd[n] : pc[n];
+                            const uint32_t ff = w ? fb2 : fa2;
+                            const long long at = row_off(lr) + ce;
+                            const int gy = y0 + lr - 2, gx = ox + ce;
+                            V2 ox2, oy2;
+                            ox2.x = pe.x, ox2.y = po.x, oy2.x = pe.y, oy2.y = po.y;
+                            *reinterpret_cast<V2*>(out.x + at) = ox2;
+                            *reinterpret_cast<V2*>(out.y + at) = oy2;
+                            *reinterpret_cast<unsigned short*>(out.fl + at) = (unsigned short)ff;
+                            if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {
+                                const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + gx;
+                                *reinterpret_cast<V2*>(peer_up.x + pat) = ox2;
+                                *reinterpret_cast<V2*>(peer_up.y + pat) = oy2;
+                                *reinterpret_cast<unsigned short*>(peer_up.fl + pat) = (unsigned short)ff;
+                            }
+                            if (gy >= peer_dn.row_lo && gy < peer_dn.row_hi) {
+                                const long long pat = (long long)e * peer_dn.cloth_stride + (long long)(gy - peer_dn.held_row0) * g.pitch + gx;
+                                *reinterpret_cast<V2*>(peer_dn.x + pat) = ox2;
+                                *reinterpret_cast<V2*>(peer_dn.y + pat) = oy2;
+                                *reinterpret_cast<unsigned short*>(peer_dn.fl + pat) = (unsigned short)ff;
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        using one_t = std::integral_constant<int, 1>;
+        using two_t = std::integral_constant<int, 2>;
+#pragma unroll 1
+        for (int s = 0; s < n_steps; ++s) {
+            // ---- phase alpha: A_j(p = s - 2j) = H-odd(j) + V-even(j) on rows (2p, 2p+1) x columns (2k+1, 2k+2) ----------
+            {
+                bool v[kItems];
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    const int p = s - 2 * jj[i];
+                    v[i] = on[i] && 2 * p >= rloA[i] && 2 * p < rhiA[i];  // warp-uniform (rhi is even with a bottom halo)
+                }
+                if (kWaveBoth && v[0] && v[1]) {
+                    phase_alpha(two_t{}, 0, s);
+                } else {
+                    if (v[0]) phase_alpha(one_t{}, 0, s);
+                    if (v[1]) phase_alpha(one_t{}, 1, s);
+                }
+            }
+            __syncthreads();
+            // ---- phase beta: B_j(p = s - 2j - 1) = V-odd(j) + H-even(j+1) on rows (2p+1, 2p+2) x columns (2k, 2k+1) -------
+            {
+                // V-odd(j) needs both rows inside sweep j's range; below it the rows are stale for every later pass too.
+                // Without a bottom halo the pair whose lower row does not exist still gives its upper row the H-even pass.
+                bool v[kItems];
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    const int p = s - 2 * jj[i] - 1;
+                    v[i] = on[i] && p >= 0 && 2 * p + 1 >= rloB[i] && 2 * p + 2 < rhiB[i];  // warp-uniform
+                }
+                if (kWaveBoth && v[0] && v[1]) {
+                    phase_beta(two_t{}, 0, s);
+                } else {
+                    if (v[0]) phase_beta(one_t{}, 0, s);
+                    if (v[1]) phase_beta(one_t{}, 1, s);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) e2[i] = e2[i] + 2 == RB ? 0 : e2[i] + 2;
+        }
+    }
+
+    // ---- counters: a stick live when its block state was derived is visited K times unless it tears on the way (then
+    // ---- sweep + 1 times, in acc_extra); sticks torn by the entry's H-even pass were visited once -------------------------
+    // (per thread the difference may be negative — derivation and tears of one block happen in different threads — so
+    //  the sum is formed in signed 64-bit; the grand total is non-negative)
+    long long v = ((long long)acc_live - (long long)acc_torn_post) * K + (long long)acc_extra;
+    unsigned int t = acc_torn;
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_down_sync(0xffffffffu, v, o);
+        t += __shfl_down_sync(0xffffffffu, t, o);
+    }
+    if ((tid & 31) == 0) {
+        if (v) atomicAdd(&ctr->relaxations, (unsigned long long)v);
+        if (t) {
+            atomicAdd(&ctr->torn_total, (unsigned long long)t);
+            atomicAdd(&ctr->torn_last, (unsigned long long)t);
+        }
+    }
+}
+
+}  // namespace clothgpu_impl

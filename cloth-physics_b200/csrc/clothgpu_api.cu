@@ -17,6 +17,7 @@
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
 #include "cloth_stream1.cuh"
+#include "cloth_wave.cuh"
 #include "frame_fold.h"
 
 using namespace clothgpu_impl;
@@ -83,6 +84,7 @@ struct clothgpu {
     int sweeps_per_launch = kMaxSweepsPerLaunch;
     int k1_stream = 1;       // 1: frames with one sweep take the register-streaming kernel (cloth_stream1.cuh)
     int s1_chunk_rows = 0;   // 0: chosen per launch
+    int wave_chunk_rows = 0; // 0: chosen per launch
     int s1_ring = 2;         // shared-memory prefetch ring depth of stream1_frame_kernel (0: register prefetch)
     int s1_warps_per_sm = 4 * S1_RING_CTAS;  // resident warps of stream1_frame_kernel per SM (its launch bounds)
     // All state planes and the strip epoch slots live in ONE device allocation, so a neighbouring strip (another
@@ -369,6 +371,65 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
     return strip_end_op(c);
 }
 
+// 2..8 sweeps per frame: the wavefront kernel (cloth_wave.cuh).
+template <typename T>
+int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
+    const Geom& g = c->g;
+    WavePlan pl{};
+    pl.K = u.iterations;
+    pl.h = 2 * pl.K;
+    pl.RB = 4 * pl.K + 4;
+    if (g.nx <= kWaveTW) {
+        pl.bands = 1;
+        pl.first_w = kWaveTW;
+        pl.mid_w = kWaveTW - 2 * pl.h;
+    } else {
+        pl.first_w = kWaveTW - pl.h;
+        pl.mid_w = kWaveTW - 2 * pl.h;
+        pl.bands = 1 + (g.nx - pl.first_w + pl.mid_w - 1) / pl.mid_w;
+    }
+    // Row chunks: one CTA per SM; a chunk pays 2h halo rows (trapezoid-wise) and 4K pipeline steps of ramp, so chunks
+    // should be long, but there must be about a whole number of waves of CTAs.
+    int R = c->wave_chunk_rows;
+    if (R < 2) {
+        const long long per_chunk = (long long)pl.bands * g.ensemble;
+        const long long want = std::max<long long>(1, ((long long)c->sm_count + per_chunk - 1) / per_chunk);  // chunks for ~1 wave
+        long long chunks = want;
+        // more waves while the chunks stay long
+        while ((g.own_rows + chunks - 1) / chunks > 512) chunks += want;
+        R = (int)((g.own_rows + chunks - 1) / chunks);
+        R = std::max(2 * pl.h, (R + 1) & ~1);
+    }
+    pl.chunk_rows = R;
+    pl.chunks = (g.own_rows + R - 1) / R;
+    const size_t smem = wave_smem_bytes<T>(pl.RB);
+    const int nxt = c->cur_pos ^ 1, nprev = c->cur_prev ^ 1;
+    Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
+    Planes<T> out = planes<T>(c, nxt, nprev);
+    const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
+    if (int rc = strip_begin_op(c)) return rc;
+    dim3 grid(pl.bands, pl.chunks, g.ensemble);
+    const bool pc = per_cloth != nullptr;
+    const bool drag = pc || (u.buttons & CLOTHGPU_MOUSE_DRAGGING);
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, kWaveThreads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+        return cudaSuccess;
+    };
+    if (pc)
+        CU_TRY(go(wave_frame_kernel<T, true, true>));
+    else if (drag)
+        CU_TRY(go(wave_frame_kernel<T, false, true>));
+    else
+        CU_TRY(go(wave_frame_kernel<T, false, false>));
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    c->cur_pos = nxt;
+    c->cur_prev = nprev;
+    return strip_end_op(c);
+}
+
 template <typename T>
 int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     const Geom& g = c->g;
@@ -448,6 +509,7 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     } else if (sched == CLOTHGPU_SCHED_ROWSTREAM && u0.iterations != 1) {
         sched = CLOTHGPU_SCHED_FUSED;
     }
+    if (sched == CLOTHGPU_SCHED_WAVE && (u0.iterations < 2 || u0.iterations > kMaxSweepsPerLaunch)) sched = CLOTHGPU_SCHED_FUSED;
     if (attached(c) && sched == CLOTHGPU_SCHED_STREAMING)
         return fail(CLOTHGPU_ERR_STATE, "attached strips exchange their edge rows inside the fused kernel; the streaming schedule is for detached handles");
     if (c->desc.strip_rows > 0 && !attached(c) && sched != CLOTHGPU_SCHED_STREAMING && u0.iterations > c->sweeps_per_launch)
@@ -457,6 +519,8 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         rc = launch_streaming<T>(c, u0, dev_frames);
     } else if (sched == CLOTHGPU_SCHED_ROWSTREAM) {
         rc = launch_stream1<T>(c, u0, dev_frames);
+    } else if (sched == CLOTHGPU_SCHED_WAVE) {
+        rc = launch_wave<T>(c, u0, dev_frames);
     } else {
         int left = u0.iterations, first = 1;
         rc = CLOTHGPU_OK;
@@ -624,6 +688,7 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     if (const char* s = getenv("CLOTHGPU_FUSED_VARIANT")) c->fused_variant = atoi(s);
     if (const char* s = getenv("CLOTHGPU_K1_STREAM")) c->k1_stream = atoi(s);
     if (const char* s = getenv("CLOTHGPU_S1_ROWS")) c->s1_chunk_rows = atoi(s) & ~1;
+    if (const char* s = getenv("CLOTHGPU_WAVE_ROWS")) c->wave_chunk_rows = atoi(s) & ~1;
     if (const char* s = getenv("CLOTHGPU_S1_RING")) {
         c->s1_ring = atoi(s);
         c->s1_warps_per_sm = c->s1_ring == 2 ? 4 * S1_RING_CTAS : 4 * S1_MIN_CTAS;  // (3 stages: 48 KB per CTA, 4 CTAs fit)
@@ -777,7 +842,7 @@ int clothgpu_get_info(clothgpu* c, clothgpu_info* info) {
 
 int clothgpu_set_schedule(clothgpu* c, int32_t schedule) {
     if (!c) return fail(CLOTHGPU_ERR_INVALID, "null handle");
-    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_ROWSTREAM)
+    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_WAVE)
         return fail(CLOTHGPU_ERR_INVALID, "unknown schedule %d", schedule);
     c->schedule = schedule;
     return CLOTHGPU_OK;

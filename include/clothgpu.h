@@ -64,8 +64,10 @@ typedef enum clothgpu_schedule {
     CLOTHGPU_SCHED_AUTO = 0,      /* ROWSTREAM for one-sweep frames of cloths large enough to feed it, else FUSED */
     CLOTHGPU_SCHED_STREAMING = 1, /* one Verlet launch + one launch per colour pass (4*K), in place   */
     CLOTHGPU_SCHED_FUSED = 2,     /* one launch per frame: shared-memory tiles with 2*K halos        */
-    CLOTHGPU_SCHED_ROWSTREAM = 3  /* one launch per frame, iterations == 1 only: every warp streams a 64-column window
+    CLOTHGPU_SCHED_ROWSTREAM = 3, /* one launch per frame, iterations == 1 only: every warp streams a 64-column window
                                      down the rows in registers (frames with more sweeps fall back to FUSED) */
+    CLOTHGPU_SCHED_WAVE = 4       /* one launch per frame, 2 <= iterations <= 8: rows stream through a shared-memory ring,
+                                     the sweeps pipelined along the rows (other sweep counts fall back to FUSED) */
 } clothgpu_schedule;
 
 /* Bits of the per-particle flag byte (also the layout returned by clothgpu_read_flags). */

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--ny", type=int, default=256)
     ap.add_argument("--iterations", type=int, default=1)
     ap.add_argument("--frames", type=int, default=4)
-    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream"])
+    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream", "wave"])
     a = ap.parse_args()
 
     import torch
@@ -59,7 +59,7 @@ def main():
     f.buttons = _abi.MOUSE_DRAGGING
     f.tear_length = 11.0
 
-    sched = {"auto": _abi.SCHED_AUTO, "fused": _abi.SCHED_FUSED, "rowstream": _abi.SCHED_ROWSTREAM}[a.schedule]
+    sched = {"auto": _abi.SCHED_AUTO, "fused": _abi.SCHED_FUSED, "rowstream": _abi.SCHED_ROWSTREAM, "wave": _abi.SCHED_WAVE}[a.schedule]
     s = StripCloth(a.nx, a.ny, max_iterations=K, device=dev)
     s.cloth.set_schedule(sched)
     s.write_state(x, y, px, py, fl)

@@ -10,7 +10,7 @@ import pytest
 import clothgpu
 from clothgpu import _abi
 from clothgpu._abi import (FLAG_ACTIVE, FLAG_ALIVE_H, FLAG_ALIVE_V, FLAG_HIGHLIGHT, FLAG_PIN, MOUSE_DRAGGING,
-                           SCHED_FUSED, SCHED_ROWSTREAM, SCHED_STREAMING)
+                           SCHED_FUSED, SCHED_ROWSTREAM, SCHED_STREAMING, SCHED_WAVE)
 from traces import c0_trace
 
 pytestmark = pytest.mark.gpu
@@ -94,7 +94,7 @@ def test_random_states_bit_exact(oracle, nx, ny, K):
     f.tear_length = 9.5                                           # low threshold: many tears
     f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 128.0 + 3 * nx, 164.0 + 3 * ny, 120.0 + 3 * nx, 170.0 + 3 * ny
     results = []
-    for schedule in (SCHED_STREAMING, SCHED_FUSED) + ((SCHED_ROWSTREAM,) if K == 1 else ()):
+    for schedule in (SCHED_STREAMING, SCHED_FUSED) + ((SCHED_ROWSTREAM,) if K == 1 else ()) + ((SCHED_WAVE,) if 2 <= K <= 8 else ()):
         g, o = make_pair(oracle, desc, schedule)
         g.write_state(*st)
         o.write_state(*st)
@@ -172,7 +172,7 @@ def test_live_stick_list_matches_reference_render_order(oracle):
     assert np.all(idx[:, 1] > idx[:, 0])
 
 
-@pytest.mark.parametrize("K,schedule", [(8, SCHED_FUSED), (1, SCHED_FUSED), (1, SCHED_ROWSTREAM)])
+@pytest.mark.parametrize("K,schedule", [(8, SCHED_FUSED), (8, SCHED_WAVE), (1, SCHED_FUSED), (1, SCHED_ROWSTREAM)])
 def test_ensemble_cloths_are_independent(oracle, K, schedule):
     nx, ny, E = 128, 128, 5
     desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, ensemble=E, max_iterations=K)
@@ -235,7 +235,7 @@ def _exchange_halos_same_device(upper, lower):
 
 
 @pytest.mark.parametrize("schedule,K", [(SCHED_STREAMING, 1), (SCHED_STREAMING, 3), (SCHED_FUSED, 1), (SCHED_FUSED, 3),
-                                        (SCHED_ROWSTREAM, 1)])
+                                        (SCHED_ROWSTREAM, 1), (SCHED_WAVE, 3)])
 def test_two_row_strips_equal_whole_cloth(oracle, schedule, K):
     """Strip decomposition is exact: 2 strips + ghost-row exchange == whole cloth, bit for bit."""
     nx, ny, split = 140, 120, 64
@@ -282,22 +282,30 @@ def test_full_size_1024_fused_equals_streaming_and_oracle(oracle):
     gf, gs = clothgpu.Cloth(desc), clothgpu.Cloth(desc)
     gf.set_schedule(SCHED_FUSED)
     gs.set_schedule(SCHED_STREAMING)
+    gw = clothgpu.Cloth(desc)
+    gw.set_schedule(SCHED_WAVE)
     o = oracle.OracleCloth(desc, oracle.COLOUR)
     f = _abi.default_frame(8)
     f.win_w, f.win_h = 128 + 6 * 1024 + 128, 164 + 6 * 1024 * 4
     for t in range(6):
         gf.step(f)
         gs.step(f)
+        gw.step(f)
         o.step(f, threads=8)
     assert_same_state(gf.read_state(), o.read_state(), "fused vs oracle")
+    assert_same_state(gw.read_state(), o.read_state(), "wave vs oracle")
     for t in range(40):
         gf.step(f)
         gs.step(f)
+        gw.step(f)
     assert_same_state(gf.read_state(), gs.read_state(), "fused vs streaming after 46 frames")
+    assert_same_state(gw.read_state(), gs.read_state(), "wave vs streaming after 46 frames")
+    assert gw.counters()["relaxations"] == 46 * 8 * (2 * 1024 * 1024 - 2048)
     assert gf.counters()["relaxations"] == 46 * 8 * (2 * 1024 * 1024 - 2048)
 
 
-@pytest.mark.parametrize("K,schedule", [(1, SCHED_FUSED), (1, SCHED_ROWSTREAM), (3, SCHED_FUSED), (11, SCHED_FUSED)])
+@pytest.mark.parametrize("K,schedule", [(1, SCHED_FUSED), (1, SCHED_ROWSTREAM), (3, SCHED_FUSED), (3, SCHED_WAVE),
+                                        (8, SCHED_WAVE), (11, SCHED_FUSED)])
 def test_attached_strips_exchange_inside_the_frame_kernel(oracle, K, schedule):
     """Three strips of one cloth, attached to each other: the fused kernel stores the edge rows into the neighbours'
     ghost rows itself (same-process attach = plain pointers; other processes use the IPC path, test_strips_multiproc).
@@ -361,7 +369,7 @@ def _run_strip_worker(nproc, args, timeout=300):
     assert "STRIPS-OK" in r.stdout, r.stdout[-3000:]
 
 
-@pytest.mark.parametrize("K,schedule", [(1, "fused"), (1, "rowstream"), (8, "fused")])
+@pytest.mark.parametrize("K,schedule", [(1, "fused"), (1, "rowstream"), (8, "fused"), (8, "wave")])
 def test_strips_multiproc_one_gpu_ipc(K, schedule):
     """Two processes share cuda:0: the neighbour's memory is mapped through cudaIpcOpenMemHandle (the path real
     multi-GPU runs take), rendezvous over gloo.  Rank 0 compares the gathered strips with the whole cloth."""
