@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "rowstream", "wave", "streaming"],
                     help="auto = what clothgpu_step picks itself: the row-streaming kernel for one-sweep frames, the tile kernel otherwise")
+    ap.add_argument("--iterations", type=int, default=0, help="override the workload's sweeps per frame (tuning)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extras", action="store_true", help="also time the K=1 and L2-resident variants")
@@ -245,6 +246,11 @@ def main():
         return float(t.item())
 
     wl = args.workload
+    if args.iterations > 0:
+        w_ = list(WORKLOADS[wl])
+        w_[2] = args.iterations
+        w_[5] += f" [sweeps overridden: {args.iterations}]"
+        WORKLOADS[wl] = tuple(w_)
     nx, ny, K, cloths, pin, desc_txt = WORKLOADS[wl]
     precision = _abi.F64 if args.precision == "f64" else _abi.F32
     strips = cloths == 0
@@ -361,6 +367,7 @@ def main():
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     suffix = "<double>" if args.precision == "f64" else "<float>"
     kernel = ("stream1_frame_kernel" if (K == 1 and (args.schedule == "rowstream" or (args.schedule == "auto" and nx * ny * cloths >= 256 * 256))) else
+              "wave_frame_kernel" if (args.schedule == "wave" and 2 <= K <= 8) or (args.schedule == "auto" and 6 <= K <= 8 and nx >= 192 and cloth.rows >= 256) else
               "fused_frame_kernel" if args.schedule != "streaming" else "relax_pass_kernel") + suffix
     facts = ncu_facts(wl if args.precision == "f64" and args.schedule == "auto" else None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -43,7 +43,8 @@ struct WavePlan {
     int K, h, RB;     // sweeps, halo = 2K, ring rows = 4K + 4
     int bands;        // column bands per cloth
     int first_w, mid_w;
-    int chunk_rows, chunks;
+    int columns;      // band columns = bands * ensemble
+    int span;         // row units per CTA (even)
 };
 
 template <typename T>
@@ -70,13 +71,27 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     uint16_t* stB = stA + HP * HW;
     V2* stage = reinterpret_cast<V2*>(stB + HP * HW);  // [kWaveDepth][2][4][HW]
 
-    const int e = blockIdx.z;
+    const int tid = threadIdx.x;
+    unsigned int acc_live = 0, acc_torn = 0, acc_torn_post = 0, acc_extra = 0;
+
+    // ---- the CTA's share of the work: a contiguous span of the row units of all band columns (band b of cloth e),
+    // ---- laid end to end, so that every CTA streams the same number of rows whatever the cloth's shape.  A span that
+    // ---- runs over the end of a band column continues at the top of the next one (the pipeline restarts).
+    const int rows_e = (g.own_rows + 1) & ~1;  // row units per band column (even, so chunks start on even rows)
+    const long long total_units = (long long)pl.columns * rows_e;
+    long long ucur = (long long)blockIdx.x * pl.span;
+    const long long uend = min(total_units, ucur + pl.span);
+    while (ucur < uend) {  // block-uniform
+    const int colidx = (int)(ucur / rows_e), r_start = (int)(ucur - (long long)colidx * rows_e);
+    const int r_stop = (int)min((long long)rows_e, r_start + (uend - ucur));
+    ucur += r_stop - r_start;
+    if (r_start >= g.own_rows) continue;  // the padding unit of an odd-height cloth
+    const int e = colidx / pl.bands;
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     const bool dragging = DRAG && (u.buttons & CLOTHGPU_MOUSE_DRAGGING) != 0;
-    const int tid = threadIdx.x;
 
-    // ---- band (columns) and chunk (rows) of this CTA ------------------------------------------------------------
-    const int bx = blockIdx.x;
+    // ---- band (columns) and chunk (rows) ---------------------------------------------------------------------------
+    const int bx = colidx % pl.bands;
     const int ix0 = bx == 0 ? 0 : pl.first_w + (bx - 1) * pl.mid_w;  // interior columns [ix0, ix1)
     const int ix1 = min(g.nx, bx == 0 ? pl.first_w : ix0 + pl.mid_w);
     const int ox = bx == 0 ? 0 : ix0 - h;  // band origin column
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     const bool halo_left = ox > 0, halo_right = ox + TW < g.nx;
     const int lx0 = ix0 - ox, lx1 = ix1 - ox;
     const int held_end = g.held_row0 + g.held_rows, own_end = g.own_row0 + g.own_rows;
-    const int ra = g.own_row0 + blockIdx.y * pl.chunk_rows, rb = min(ra + pl.chunk_rows, own_end);  // owned rows
+    const int ra = g.own_row0 + r_start, rb = min(g.own_row0 + r_stop, own_end);  // owned rows of this chunk
     const int y0 = max(g.held_row0, ra - h), y1 = min(held_end, rb + h);                            // rows streamed
     const bool halo_top = y0 > g.held_row0, halo_bottom = y1 < held_end;
     const int n_lr = y1 - y0 + 2;  // local rows: 0, 1 = dummy zero pair, real rows [2, n_lr)
@@ -95,7 +110,6 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     };
     auto slot = [&](int lr) -> int { return lr % RB; };
 
-    unsigned int acc_live = 0, acc_torn = 0, acc_torn_post = 0, acc_extra = 0;
     auto owned = [&](int lr, int c) -> bool { return lr >= ly0 && lr < ly1 && c >= lx0 && c < lx1; };
     // a torn stick (after the block states were derived): clear the alive bit of its head's flag byte
     auto tear = [&](int lr, int c, uint32_t alive_bit, int sweep) {
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             __syncthreads();  // end of phase beta
             eslot = eslot + 2 == RB ? 0 : eslot + 2;
         }
+        cp_async_wait<0>();  // nothing may still be landing in the staging slots when the next chunk starts
     } else {
         // =============================== worker warps ==============================================================
         // A thread works for the same (at most two) sweep stages and the same column pair during the whole launch, so
@@ -466,6 +481,9 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             for (int i = 0; i < kItems; ++i) e2[i] = e2[i] + 2 == RB ? 0 : e2[i] + 2;
         }
     }
+
+    __syncthreads();  // the ring and the staging slots are reused by the next chunk
+    }  // chunks of this CTA
 
     // ---- counters: a stick live when its block state was derived is visited K times unless it tears on the way (then
     // ---- sweep + 1 times, in acc_extra); sticks torn by the entry's H-even pass were visited once -------------------------

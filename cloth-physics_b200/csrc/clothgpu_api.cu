@@ -85,6 +85,7 @@ struct clothgpu {
     int k1_stream = 1;       // 1: frames with one sweep take the register-streaming kernel (cloth_stream1.cuh)
     int s1_chunk_rows = 0;   // 0: chosen per launch
     int wave_chunk_rows = 0; // 0: chosen per launch
+    int wave_auto = 1;       // AUTO may pick the wavefront kernel
     int s1_ring = 2;         // shared-memory prefetch ring depth of stream1_frame_kernel (0: register prefetch)
     int s1_warps_per_sm = 4 * S1_RING_CTAS;  // resident warps of stream1_frame_kernel per SM (its launch bounds)
     // All state planes and the strip epoch slots live in ONE device allocation, so a neighbouring strip (another
@@ -388,27 +389,28 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
         pl.mid_w = kWaveTW - 2 * pl.h;
         pl.bands = 1 + (g.nx - pl.first_w + pl.mid_w - 1) / pl.mid_w;
     }
-    // Row chunks: one CTA per SM; a chunk pays 2h halo rows (trapezoid-wise) and 4K pipeline steps of ramp, so chunks
-    // should be long, but there must be about a whole number of waves of CTAs.
-    int R = c->wave_chunk_rows;
-    if (R < 2) {
-        const long long per_chunk = (long long)pl.bands * g.ensemble;
-        const long long want = std::max<long long>(1, ((long long)c->sm_count + per_chunk - 1) / per_chunk);  // chunks for ~1 wave
-        long long chunks = want;
-        // more waves while the chunks stay long
-        while ((g.own_rows + chunks - 1) / chunks > 512) chunks += want;
-        R = (int)((g.own_rows + chunks - 1) / chunks);
-        R = std::max(2 * pl.h, (R + 1) & ~1);
+    // Work split: the row units of all band columns laid end to end, cut into equal spans, one per CTA, a whole number
+    // of CTAs per SM (one CTA is resident per SM).  A span pays 2h halo rows (trapezoid-wise) and ~2K pipeline steps of
+    // ramp per chunk it touches, so spans should be long; several waves only when the spans stay long anyway.
+    pl.columns = pl.bands * g.ensemble;
+    const long long rows_e = (g.own_rows + 1) & ~1;
+    const long long total = (long long)pl.columns * rows_e;
+    long long span = c->wave_chunk_rows;
+    if (span < 2) {
+        long long ctas = c->sm_count;
+        while (total / ctas > 640) ctas += c->sm_count;
+        span = (total + ctas - 1) / ctas;
+        span = std::max<long long>(2 * pl.h, (span + 1) & ~1ll);
     }
-    pl.chunk_rows = R;
-    pl.chunks = (g.own_rows + R - 1) / R;
+    pl.span = (int)std::min<long long>(span, rows_e * (long long)pl.columns);
+    const unsigned n_ctas = (unsigned)((total + pl.span - 1) / pl.span);
     const size_t smem = wave_smem_bytes<T>(pl.RB);
     const int nxt = c->cur_pos ^ 1, nprev = c->cur_prev ^ 1;
     Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
     Planes<T> out = planes<T>(c, nxt, nprev);
     const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
     if (int rc = strip_begin_op(c)) return rc;
-    dim3 grid(pl.bands, pl.chunks, g.ensemble);
+    dim3 grid(n_ctas);
     const bool pc = per_cloth != nullptr;
     const bool drag = pc || (u.buttons & CLOTHGPU_MOUSE_DRAGGING);
     auto go = [&](auto kernel) -> cudaError_t {
@@ -503,9 +505,16 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, sizeof(unsigned long long), c->stream));
     int sched = c->schedule;
     if (sched == CLOTHGPU_SCHED_AUTO) {
-        // small cloths cannot feed enough independent warps to the row-streaming kernel; they take the tile kernel
+        // One sweep: the row-streaming kernel, unless the cloth is too small to feed enough independent warps.
+        // 6..8 sweeps on cloths that fill the 256-column bands and amortise the pipeline ramp: the wavefront kernel
+        // (measured on 4096^2: slower than the tile kernel up to 4 sweeps, level at 6, 1.19x faster at 8).
         const long long warps = (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble;
-        sched = (u0.iterations == 1 && c->k1_stream && warps >= 2ll * c->sm_count) ? CLOTHGPU_SCHED_ROWSTREAM : CLOTHGPU_SCHED_FUSED;
+        if (u0.iterations == 1 && c->k1_stream && warps >= 2ll * c->sm_count)
+            sched = CLOTHGPU_SCHED_ROWSTREAM;
+        else if (u0.iterations >= 6 && u0.iterations <= kMaxSweepsPerLaunch && c->wave_auto && c->g.nx >= 192 && c->g.own_rows >= 256)
+            sched = CLOTHGPU_SCHED_WAVE;
+        else
+            sched = CLOTHGPU_SCHED_FUSED;
     } else if (sched == CLOTHGPU_SCHED_ROWSTREAM && u0.iterations != 1) {
         sched = CLOTHGPU_SCHED_FUSED;
     }
@@ -689,6 +698,7 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     if (const char* s = getenv("CLOTHGPU_K1_STREAM")) c->k1_stream = atoi(s);
     if (const char* s = getenv("CLOTHGPU_S1_ROWS")) c->s1_chunk_rows = atoi(s) & ~1;
     if (const char* s = getenv("CLOTHGPU_WAVE_ROWS")) c->wave_chunk_rows = atoi(s) & ~1;
+    if (const char* s = getenv("CLOTHGPU_WAVE_AUTO")) c->wave_auto = atoi(s);
     if (const char* s = getenv("CLOTHGPU_S1_RING")) {
         c->s1_ring = atoi(s);
         c->s1_warps_per_sm = c->s1_ring == 2 ? 4 * S1_RING_CTAS : 4 * S1_MIN_CTAS;  // (3 stages: 48 KB per CTA, 4 CTAs fit)
