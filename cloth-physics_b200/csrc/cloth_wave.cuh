@@ -124,10 +124,26 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         xyE[i] = z, xyO[i] = z;  // rows 0 and 1 are slots 0 and 1
     }
     for (int i = tid; i < 2 * TW; i += kWaveThreads) fl8[i] = 0;
-    // (stA/stB of pair 0 are never read: A_j(0) is skipped, B_j(0) of stage 0 derives its own)
+    // (stA of pair 0 is never read: A_j(0) is skipped; stB of pair 0 is written by the entry warps at step 0)
 
     const int last_pair = (n_lr + 1) >> 1;  // entry also delivers one all-zero pair past the end (row n_lr may be a B tail)
     const int n_steps = last_pair + 2 * K + 1;
+
+    // ---- the state word of a 2x2 block (cloth_fused.cuh): live bits of its four sticks, pin bits of its corners ------
+    auto live_bit = [](uint32_t fh, uint32_t ft, uint32_t alive) -> uint32_t {
+        return ((fh & alive) && (fh & ft & CLOTHGPU_FLAG_ACTIVE)) ? 1u : 0u;  // cloth.go:97
+    };
+    auto pack = [&](uint32_t fa, uint32_t fb, uint32_t fc, uint32_t fd, uint32_t first_alive, uint32_t second_alive,
+                    bool first_ok) -> uint32_t {
+        uint32_t st = 0;
+        if (first_ok) st |= live_bit(fa, fb, first_alive) | (live_bit(fc, fd, first_alive) << 1);
+        st |= (live_bit(fa, fc, second_alive) << 2) | (live_bit(fb, fd, second_alive) << 3);
+        const uint32_t pa = fa & CLOTHGPU_FLAG_PIN, pb = fb & CLOTHGPU_FLAG_PIN, pc = fc & CLOTHGPU_FLAG_PIN,
+                       pd = fd & CLOTHGPU_FLAG_PIN;  // CLOTHGPU_FLAG_PIN == 1
+        st |= (pa << 4) | (pb << 5) | (pc << 6) | (pd << 7);
+        st |= (pa << 8) | (pc << 9) | (pb << 10) | (pd << 11);
+        return st;
+    };
 
     if (tid >= kWaveWorkers) {
         // =============================== entry warps ===============================================================
@@ -163,6 +179,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         uint32_t fnext[2] = {load_flags(1, 0), load_flags(1, 1)};
         __syncthreads();  // (matches the workers' prologue barrier)
         int eslot = 2;  // ring slot of local row 2q (q = 1 at the first step)
+        uint32_t fprev[2] = {0u, 0u};  // flags of the previous pair's second row (columns 2et, 2et+1); the dummy pair has none
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
             const int q = s + 1;  // the pair delivered during this step
@@ -231,6 +248,25 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     xyO[sl * HW + et] = p1[row];
                     *reinterpret_cast<uint16_t*>(fl8 + sl * TW + c) = (uint16_t)(f0[row] | (f1[row] << 8));
                 }
+                // ---- block states of this pair, derived HERE and not by sweep stage 0: the entry warps have the flags in
+                // ---- registers and time to spare, and every worker group then does the same amount of work per step ----
+                asm volatile("bar.sync 1, %0;" ::"n"(kWaveEntry) : "memory");  // the entry warps' flag bytes are in the ring
+                {   // group A, pair q: rows (2q, 2q+1) x columns (2et+1, 2et+2); heads a (H, V), c (H), b (V)
+                    const int er = (et + 1) & (HW - 1), cl = c + 1, cr = 2 * er;
+                    const uint32_t fb = fl8[eslot * TW + cr], fd = fl8[(eslot + 1) * TW + cr];
+                    const uint32_t st = pack(f1[0], fb, f1[1], fd, CLOTHGPU_FLAG_ALIVE_H, CLOTHGPU_FLAG_ALIVE_V, et + 1 < HW);
+                    stA[(eslot >> 1) * HW + et] = (uint16_t)st;
+                    const bool oa = owned(2 * q, cl), oc = owned(2 * q + 1, cl), ob = owned(2 * q, cr);
+                    acc_live += (oa ? (st & 1u) + ((st >> 2) & 1u) : 0u) + (oc ? (st >> 1) & 1u : 0u) + (ob ? (st >> 3) & 1u : 0u);
+                }
+                {   // group B, pair q-1: rows (2q-1, 2q) x columns (2et, 2et+1); heads a (V, H), c (V), b (H)
+                    const int s2p = eslot == 0 ? RB - 2 : eslot - 2;  // slot of row 2(q-1)
+                    const uint32_t st = pack(fprev[0], f0[0], fprev[1], f1[0], CLOTHGPU_FLAG_ALIVE_V, CLOTHGPU_FLAG_ALIVE_H, true);
+                    stB[(s2p >> 1) * HW + et] = (uint16_t)st;
+                    const bool oa = owned(2 * q - 1, c), oc = owned(2 * q - 1, c + 1), ob = owned(2 * q, c);
+                    acc_live += (oa ? (st & 1u) + ((st >> 2) & 1u) : 0u) + (oc ? (st >> 1) & 1u : 0u) + (ob ? (st >> 3) & 1u : 0u);
+                }
+                fprev[0] = f0[1], fprev[1] = f1[1];
             }
             __syncthreads();  // end of phase alpha
             __syncthreads();  // end of phase beta
@@ -263,20 +299,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             rloB[i] = halo_top ? 2 + 2 * j : 0, rhiB[i] = halo_bottom ? n_lr - 2 * j : n_lr + 1;
         }
         __syncthreads();  // prologue: the dummy pair is in place
-        auto live_bit = [](uint32_t fh, uint32_t ft, uint32_t alive) -> uint32_t {
-            return ((fh & alive) && (fh & ft & CLOTHGPU_FLAG_ACTIVE)) ? 1u : 0u;  // cloth.go:97
-        };
-        auto pack = [&](uint32_t fa, uint32_t fb, uint32_t fc, uint32_t fd, uint32_t first_alive, uint32_t second_alive,
-                        bool first_ok) -> uint32_t {
-            uint32_t st = 0;
-            if (first_ok) st |= live_bit(fa, fb, first_alive) | (live_bit(fc, fd, first_alive) << 1);
-            st |= (live_bit(fa, fc, second_alive) << 2) | (live_bit(fb, fd, second_alive) << 3);
-            const uint32_t pa = fa & CLOTHGPU_FLAG_PIN, pb = fb & CLOTHGPU_FLAG_PIN, pc = fc & CLOTHGPU_FLAG_PIN,
-                           pd = fd & CLOTHGPU_FLAG_PIN;  // CLOTHGPU_FLAG_PIN == 1
-            st |= (pa << 4) | (pb << 5) | (pc << 6) | (pd << 7);
-            st |= (pa << 8) | (pc << 9) | (pb << 10) | (pd << 11);
-            return st;
-        };
+        using pins_none_t = std::integral_constant<int, kPinsNone>;
+        using pins_each_t = std::integral_constant<int, kPinsEach>;
         // One phase for NI of this thread's items at once (2 * NI sticks in flight per pass: the relaxation of a stick is
         // one long dependent binary64 chain, and with 4 worker warps per scheduler the pipe needs the extra chains).
         auto phase_alpha = [&](auto ni, int i0, int s) {
@@ -291,36 +315,33 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 jn[n] = jj[i], pp[n] = s - 2 * jj[i], sa[n] = e2[i];  // slots of rows 2p, 2p+1 = sa, sa+1; state slot sa/2
                 const int sb = sa[n] + 1;
                 pa[n] = xyO[sa[n] * HW + k], pb[n] = xyE[sa[n] * HW + kr], pc[n] = xyO[sb * HW + k], pd[n] = xyE[sb * HW + kr];
-                if (jn[n] == 0) {  // derive the block state from the flag bytes (warp-uniform branch)
-                    const uint32_t fa = fl8[sa[n] * TW + cl], fb = fl8[sa[n] * TW + cr], fc = fl8[sb * TW + cl], fd = fl8[sb * TW + cr];
-                    st[n] = pack(fa, fb, fc, fd, CLOTHGPU_FLAG_ALIVE_H, CLOTHGPU_FLAG_ALIVE_V, k + 1 < HW);
-                    stA[(sa[n] >> 1) * HW + k] = (uint16_t)st[n];
-                    // sticks headed by an owned particle: a (H, V), c (H), b (V)
-                    const bool oa = owned(2 * pp[n], cl), oc = owned(2 * pp[n] + 1, cl), ob = owned(2 * pp[n], cr);
-                    acc_live += (oa ? (st[n] & 1u) + ((st[n] >> 2) & 1u) : 0u) + (oc ? (st[n] >> 1) & 1u : 0u) + (ob ? (st[n] >> 3) & 1u : 0u);
-                } else {
-                    st[n] = stA[(sa[n] >> 1) * HW + k];
-                }
+                st[n] = stA[(sa[n] >> 1) * HW + k];  // (derived by the entry warps when the pair arrived)
                 const uint32_t sm = st[n] & maskA[i];
                 live1 |= (sm & 3u) << (2 * n), live2 |= ((sm >> 2) & 3u) << (2 * n);
                 pins1 |= ((st[n] >> 4) & 15u) << (4 * n), pins2 |= ((st[n] >> 8) & 15u) << (4 * n);
             }
             bool touched = false;
-            uint32_t tore1, tore2;
-            {  // H-odd: a->b and c->d
-                V2* hh[NS];
-                V2* tt[NS];
+            uint32_t tore1 = 0, tore2 = 0;
+            auto passes = [&](auto pm) {
+                constexpr int PM = decltype(pm)::value;
+                {  // H-odd: a->b and c->d
+                    V2* hh[NS];
+                    V2* tt[NS];
 #pragma unroll
-                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
-                tore1 = relax_n<T, DRAG, NS>(hh, tt, live1, pins1, u, dragging, touched);
-            }
-            {  // V-even: a->c and b->d
-                V2* hh[NS];
-                V2* tt[NS];
+                    for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
+                    tore1 = relax_n<T, DRAG, NS, PM>(hh, tt, live1, pins1, u, dragging, touched);
+                }
+                {  // V-even: a->c and b->d
+                    V2* hh[NS];
+                    V2* tt[NS];
 #pragma unroll
-                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
-                tore2 = relax_n<T, DRAG, NS>(hh, tt, live2, pins2, u, dragging, touched);
-            }
+                    for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
+                    tore2 = relax_n<T, DRAG, NS, PM>(hh, tt, live2, pins2, u, dragging, touched);
+                }
+            };
+            // pinned particles are rare (the cloth's pinned rows): one vote per item picks the pass code without pin logic
+            if (__any_sync(0xffffffffu, (pins1 | pins2) != 0u)) passes(pins_each_t{});
+            else passes(pins_none_t{});
             if (DRAG && (tore1 | tore2)) {  // rare
 #pragma unroll
                 for (int n = 0; n < NI; ++n) {
@@ -356,38 +377,33 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 const int s2p = e2[i] == 0 ? RB - 2 : e2[i] - 2;  // slot of row 2p (this pair is one behind A's)
                 sa[n] = s2p + 1, sb[n] = e2[i];
                 pa[n] = xyE[sa[n] * HW + k], pc[n] = xyO[sa[n] * HW + k], pb[n] = xyE[sb[n] * HW + k], pd[n] = xyO[sb[n] * HW + k];
-                if (jn[n] == 0) {
-                    const uint32_t fa2 = *reinterpret_cast<const uint16_t*>(fl8 + sa[n] * TW + ce);
-                    const uint32_t fb2 = *reinterpret_cast<const uint16_t*>(fl8 + sb[n] * TW + ce);
-                    st[n] = pack(fa2 & 0xffu, fb2 & 0xffu, fa2 >> 8, fb2 >> 8, CLOTHGPU_FLAG_ALIVE_V, CLOTHGPU_FLAG_ALIVE_H, true);
-                    stB[(s2p >> 1) * HW + k] = (uint16_t)st[n];
-                    // heads: a = (2p+1, ce) (V, H), c = (2p+1, co) (V), b = (2p+2, ce) (H)
-                    const bool oa = owned(2 * pp[n] + 1, ce), oc = owned(2 * pp[n] + 1, co), ob = owned(2 * pp[n] + 2, ce);
-                    acc_live += (oa ? (st[n] & 1u) + ((st[n] >> 2) & 1u) : 0u) + (oc ? (st[n] >> 1) & 1u : 0u) + (ob ? (st[n] >> 3) & 1u : 0u);
-                } else {
-                    st[n] = stB[(s2p >> 1) * HW + k];
-                }
+                st[n] = stB[(s2p >> 1) * HW + k];
                 const uint32_t sm = st[n] & maskB[i];  // (the last sweep's mask has no second-pass bits)
                 live1 |= (sm & 3u) << (2 * n), live2 |= ((sm >> 2) & 3u) << (2 * n);
                 pins1 |= ((st[n] >> 4) & 15u) << (4 * n), pins2 |= ((st[n] >> 8) & 15u) << (4 * n);
                 any_mid |= jn[n] + 1 < K;
             }
             bool touched = false;
-            uint32_t tore1, tore2 = 0;
-            {  // V-odd: a->b and c->d
-                V2* hh[NS];
-                V2* tt[NS];
+            uint32_t tore1 = 0, tore2 = 0;
+            auto passes = [&](auto pm) {
+                constexpr int PM = decltype(pm)::value;
+                {  // V-odd: a->b and c->d
+                    V2* hh[NS];
+                    V2* tt[NS];
 #pragma unroll
-                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
-                tore1 = relax_n<T, DRAG, NS>(hh, tt, live1, pins1, u, dragging, touched);
-            }
-            if (any_mid) {  // H-even of the next sweep: a->c and b->d (warp-uniform)
-                V2* hh[NS];
-                V2* tt[NS];
+                    for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
+                    tore1 = relax_n<T, DRAG, NS, PM>(hh, tt, live1, pins1, u, dragging, touched);
+                }
+                if (any_mid) {  // H-even of the next sweep: a->c and b->d (warp-uniform)
+                    V2* hh[NS];
+                    V2* tt[NS];
 #pragma unroll
-                for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
-                tore2 = relax_n<T, DRAG, NS>(hh, tt, live2, pins2, u, dragging, touched);
-            }
+                    for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
+                    tore2 = relax_n<T, DRAG, NS, PM>(hh, tt, live2, pins2, u, dragging, touched);
+                }
+            };
+            if (__any_sync(0xffffffffu, (pins1 | pins2) != 0u)) passes(pins_each_t{});
+            else passes(pins_none_t{});
             if (DRAG && (tore1 | tore2)) {  // rare
 #pragma unroll
                 for (int n = 0; n < NI; ++n) {
