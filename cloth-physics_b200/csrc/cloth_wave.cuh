@@ -33,6 +33,28 @@ namespace clothgpu_impl {
 constexpr int kWaveTW = 256, kWaveHW = 128;
 constexpr int kWaveWorkers = 512, kWaveEntry = 128, kWaveThreads = kWaveWorkers + kWaveEntry;
 constexpr int kWaveGroups = kWaveWorkers / 64;  // worker groups of 64 column pairs
+#ifndef WAVE_SETS
+#define WAVE_SETS 2
+#endif
+#ifndef WAVE_STAGGER
+#define WAVE_STAGGER 0
+#endif
+// Two worker sets: set X (groups 0-3, with the entry warps) runs the first half of the sweep stages, set Y (groups 4-7) the
+// second half.  Each set has its own pair of barriers per step; the sets are chained by two producer/consumer barriers
+// ("X has finished step s", "Y has finished step s": bar.arrive / bar.sync), so they may drift apart by up to one step and
+// one set's barrier waits, loads and address arithmetic overlap the other set's binary64 work on the same scheduler.
+constexpr int kWaveSets = WAVE_SETS;
+constexpr bool kWaveStagger = WAVE_STAGGER != 0;  // Y may start step s only after X's alpha phase of step s
+constexpr int kBarEntry = 1, kBarX = 2, kBarY = 3, kBarXDone = 4 /* .. 7 */, kBarYDone = 8 /* .. 11 */;
+constexpr int kWaveSetThreads = kWaveWorkers / 2;
+
+#ifdef WAVE_ABLATE_BAR  // timing experiment only (results are wrong): what do the barriers cost?
+__device__ __forceinline__ void bar_sync(int, int) {}
+__device__ __forceinline__ void bar_arrive(int, int) {}
+#else
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+#endif
 constexpr int kWaveDepth = 3;                   // row pairs in flight in the staging ring
 #ifndef WAVE_BOTH
 #define WAVE_BOTH 0
@@ -183,6 +205,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
             const int q = s + 1;  // the pair delivered during this step
+            // the slots refilled in this step held the pair that set Y wrote back in step s - 2
+            if (kWaveSets == 2 && s >= 2) bar_sync(kBarYDone + ((s - 2) & 3), kWaveSetThreads + kWaveEntry);
             if (q <= last_pair) {
                 cp_async_wait<kWaveDepth - 1>();
                 const uint32_t fcur[2] = {fnext[0], fnext[1]};
@@ -250,7 +274,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 }
                 // ---- block states of this pair, derived HERE and not by sweep stage 0: the entry warps have the flags in
                 // ---- registers and time to spare, and every worker group then does the same amount of work per step ----
-                asm volatile("bar.sync 1, %0;" ::"n"(kWaveEntry) : "memory");  // the entry warps' flag bytes are in the ring
+                bar_sync(kBarEntry, kWaveEntry);  // the entry warps' flag bytes are in the ring
                 {   // group A, pair q: rows (2q, 2q+1) x columns (2et+1, 2et+2); heads a (H, V), c (H), b (V)
                     const int er = (et + 1) & (HW - 1), cl = c + 1, cr = 2 * er;
                     const uint32_t fb = fl8[eslot * TW + cr], fd = fl8[(eslot + 1) * TW + cr];
@@ -268,8 +292,13 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 }
                 fprev[0] = f0[1], fprev[1] = f1[1];
             }
-            __syncthreads();  // end of phase alpha
-            __syncthreads();  // end of phase beta
+            if (kWaveSets == 2) {
+                bar_sync(kBarX, kWaveSetThreads + kWaveEntry);  // end of set X's phase alpha
+                bar_sync(kBarX, kWaveSetThreads + kWaveEntry);  // end of set X's phase beta
+            } else {
+                __syncthreads();  // end of phase alpha
+                __syncthreads();  // end of phase beta
+            }
             eslot = eslot + 2 == RB ? 0 : eslot + 2;
         }
         cp_async_wait<0>();  // nothing may still be landing in the staging slots when the next chunk starts
@@ -279,6 +308,9 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         // everything that depends on them is computed once: column masks, row ranges, and the ring slots advance by two
         // rows per step.
         const int grp = tid >> 6, k64 = tid & 63;
+        const int set = kWaveSets == 2 ? grp >> 2 : 0;           // 0 = X, 1 = Y
+        const int Kx = kWaveSets == 2 ? (K + 1) >> 1 : K;        // stages [0, Kx) belong to X, [Kx, K) to Y
+        const int set_j0 = set ? Kx : 0, set_nj = set ? K - Kx : Kx;
         const int k = (grp & 1) * 64 + k64, kr = (k + 1) & (HW - 1);
         const int cl = 2 * k + 1, cr = 2 * kr, ce = 2 * k, co = ce + 1;
         constexpr int kItems = 2;  // ceil(2 * 8 / kWaveGroups)
@@ -287,9 +319,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         bool on[kItems];
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
-            const int j = (grp >> 1) + i * (kWaveGroups / 2);
+            const int jl = kWaveSets == 2 ? ((grp & 3) >> 1) + 2 * i : (grp >> 1) + i * (kWaveGroups / 2);  // stage within the set
+            const int j = set_j0 + jl;
             jj[i] = j;
-            on[i] = j < K;
+            on[i] = jl < set_nj;
             e2[i] = j == 0 ? 0 : RB - 4 * j;  // slot of row 2p for p = -2j (step 0); 4j < RB
             const int c0 = halo_left ? 2 * j : 0, c1 = halo_right ? TW - 2 * j : cols;              // sweep j's columns
             const int d0 = halo_left ? 2 * j + 2 : 0, d1 = halo_right ? TW - 2 * j - 2 : cols;      // sweep j+1's columns
@@ -355,7 +388,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     }
                 }
             }
-            if (touched) {
+            {   // (written back even when no stick moved: a store costs less than the branch around it)
 #pragma unroll
                 for (int n = 0; n < NI; ++n) {
                     const int sb = sa[n] + 1;
@@ -420,7 +453,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
 #pragma unroll
             for (int n = 0; n < NI; ++n) {
                 if (jn[n] + 1 < K) {
-                    if (touched) xyE[sa[n] * HW + k] = pa[n], xyO[sa[n] * HW + k] = pc[n], xyE[sb[n] * HW + k] = pb[n], xyO[sb[n] * HW + k] = pd[n];
+                    xyE[sa[n] * HW + k] = pa[n], xyO[sa[n] * HW + k] = pc[n], xyE[sb[n] * HW + k] = pb[n], xyO[sb[n] * HW + k] = pd[n];
                 } else if (ce >= lx0 && ce < lx1) {
                     // ---- the last colour pass is done: rows 2p+1 and 2p+2 leave through the registers --------------------------
                     const uint32_t fa2 = *reinterpret_cast<const uint16_t*>(fl8 + sa[n] * TW + ce);  // (after possible tears of this pass)
@@ -459,6 +492,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         using two_t = std::integral_constant<int, 2>;
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
+            // set Y's first stage reads what set X's last stage finished in step s - 1
+            if (kWaveSets == 2 && set == 1 && s >= 1) bar_sync(kBarXDone + ((s - 1) & 3), kWaveWorkers);
             // ---- phase alpha: A_j(p = s - 2j) = H-odd(j) + V-even(j) on rows (2p, 2p+1) x columns (2k+1, 2k+2) ----------
             {
                 bool v[kItems];
@@ -474,7 +509,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     if (v[1]) phase_alpha(one_t{}, 1, s);
                 }
             }
-            __syncthreads();
+            if (kWaveSets == 2) {
+                bar_sync(set ? kBarY : kBarX, set ? kWaveSetThreads : kWaveSetThreads + kWaveEntry);
+                if (kWaveStagger && set == 0 && s >= 1) bar_arrive(kBarXDone + ((s - 1) & 3), kWaveWorkers);
+            } else {
+                __syncthreads();
+            }
             // ---- phase beta: B_j(p = s - 2j - 1) = V-odd(j) + H-even(j+1) on rows (2p+1, 2p+2) x columns (2k, 2k+1) -------
             {
                 // V-odd(j) needs both rows inside sweep j's range; below it the rows are stale for every later pass too.
@@ -492,7 +532,16 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     if (v[1]) phase_beta(one_t{}, 1, s);
                 }
             }
-            __syncthreads();
+            if (kWaveSets == 2) {
+                bar_sync(set ? kBarY : kBarX, set ? kWaveSetThreads : kWaveSetThreads + kWaveEntry);
+                if (set == 0) {
+                    if (!kWaveStagger && s + 1 < n_steps) bar_arrive(kBarXDone + (s & 3), kWaveWorkers);  // X has finished step s
+                } else if (s + 2 < n_steps) {
+                    bar_arrive(kBarYDone + (s & 3), kWaveSetThreads + kWaveEntry);  // Y has finished step s: its slots may be refilled
+                }
+            } else {
+                __syncthreads();
+            }
 #pragma unroll
             for (int i = 0; i < kItems; ++i) e2[i] = e2[i] + 2 == RB ? 0 : e2[i] + 2;
         }
