@@ -328,74 +328,163 @@ __global__ void __launch_bounds__(1024)
     if (threadIdx.x == 0) *total_out = carry;
 }
 
-// Scatter: one block per kSegBlock particles (the unit segment_count_kernel counted), walked in 16 sub-tiles of 256
-// with a running offset; inside a sub-tile the sticks are ranked with warp ballots.
+// Scatter: one block per kSegBlock particles (the unit segment_count_kernel counted).  Every warp owns 512 consecutive
+// particles of the block.  It loads their flag bytes and those of the row above once (16 bytes per lane), keeps them in
+// shared memory and counts the sticks as the count kernel does; one block barrier turns the eight warp totals into warp
+// offsets, and from there on the warps run independently: 32 particles per trip, flags from shared memory, the coordinate
+// loads of the next trip in flight while this trip's sticks are ranked with two ballots, converted and staged in a
+// warp-private buffer at their rank, then copied out as ONE contiguous, fully coalesced run of float4 (before ranking the
+// sticks of consecutive lanes are not adjacent in the output: a lane has 0, 1 or 2 of them).
 template <typename T>
 __global__ void __launch_bounds__(kStreamThreads)
     segment_write_kernel(Planes<T> P, Geom g, int cloth, const unsigned int* __restrict__ block_offsets,
                          float4* __restrict__ xyxy, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
                          unsigned long long cap) {
-    __shared__ unsigned int warp_base[kStreamThreads / 32 + 1];
+    constexpr int kWarps = kStreamThreads / 32, kPerWarp = kSegBlock / kWarps, kTrips = kPerWarp / 32;
+    static_assert(kPerWarp == 32 * 16, "one uint4 of flag bytes per lane");
+    __shared__ unsigned int warp_tot[kWarps];
+    __shared__ __align__(16) uint8_t s_f[kWarps][kPerWarp + 16];   // [15] = the particle left of the warp's first one
+    __shared__ __align__(16) uint8_t s_fu[kWarps][kPerWarp];
+    __shared__ float4 s_xy[kWarps][64];
+    __shared__ uint2 s_idx[kWarps][64];
+    // the highlight bytes of all sticks of the warp (at most 1024), shifted so that shared and global addresses agree
+    // mod 16: they leave as 128-bit stores at the end instead of two one-byte stores per lane and trip
+    __shared__ __align__(16) uint8_t s_hl[kWarps][2 * kPerWarp + 16];
     const long long n = (long long)g.own_rows * g.pitch;
     const long long base = (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t below = (1u << lane) - 1u;
-    unsigned long long run = block_offsets[blockIdx.x];
-#pragma unroll 1
-    for (int sub = 0; sub < kSegPerThread; ++sub) {
-        const long long i = (long long)blockIdx.x * kSegBlock + sub * kStreamThreads + threadIdx.x;
-        if ((long long)blockIdx.x * kSegBlock + sub * kStreamThreads >= n) break;  // block-uniform
-        bool v = false, h = false;
-        int ly = 0, cx = 0;
-        uint32_t f = 0, fu = 0, fw = 0;
-        if (i < n) {
-            ly = (int)(i / g.pitch);
-            cx = (int)(i - (long long)ly * g.pitch);
-            f = P.fl[base + i];
+    const long long warp_first = (long long)blockIdx.x * kSegBlock + (long long)w * kPerWarp;
+    const uint8_t* fl = P.fl + base;
+    const T* X = P.x + base;
+    const T* Y = P.y + base;
+
+    {   // ---- flags of this warp's 512 particles -> shared memory; their sticks (segment_count_kernel's tests) -----------
+        constexpr uint32_t k1 = 0x01010101u;
+        const long long off = warp_first + lane * 16;
+        unsigned int cnt = 0;
+        uint4 w4 = make_uint4(0, 0, 0, 0), u4 = make_uint4(0, 0, 0, 0);
+        uint32_t left = 0;
+        if (off < n) {
+            const int ly = (int)(off / g.pitch), cx = (int)(off - (long long)ly * g.pitch);
+            w4 = *reinterpret_cast<const uint4*>(fl + off);
+            if (g.own_row0 + ly > g.held_row0) u4 = *reinterpret_cast<const uint4*>(fl + off - g.pitch);
+            if (cx > 0) left = fl[off - 1];
+            const uint32_t wq[4] = {w4.x, w4.y, w4.z, w4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
+            uint32_t carry = left;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t f = wq[q], act = (f >> 1) & k1;
+                const uint32_t fl_left = (f << 8) | (carry & 0xffu);
+                cnt += __popc(act & (up[q] >> 4) & (up[q] >> 1) & k1) + __popc(act & (fl_left >> 3) & (fl_left >> 1) & k1);
+                carry = f >> 24;
+            }
+        }
+        *reinterpret_cast<uint4*>(&s_f[w][16 + lane * 16]) = w4;
+        *reinterpret_cast<uint4*>(&s_fu[w][lane * 16]) = u4;
+        if (lane == 0) s_f[w][15] = (uint8_t)left;  // (0 when the first particle starts a row: no stick to its left)
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        if (lane == 0) warp_tot[w] = cnt;
+    }
+    __syncthreads();
+    // (output positions fit 32 bits: the host side rejects cloths with 2^32 or more possible sticks)
+    unsigned int run = block_offsets[blockIdx.x];
+    for (int k = 0; k < w; ++k) run += warp_tot[k];
+    const unsigned int cap32 = (unsigned int)min(cap, 0xffffffffull);
+    const unsigned int run0 = run, hl_shift = run0 & 15u;  // (hl itself is 16-byte aligned)
+    unsigned int hl_at = hl_shift;                         // where this trip's highlight bytes go in s_hl[w]
+
+    // rows and columns in 32-bit arithmetic: one division per lane, then every trip advances the lane by 32 particles
+    const int row0 = (int)(warp_first / g.pitch), cx0 = (int)(warp_first - (long long)row0 * g.pitch);
+    const int n_here = (int)min((long long)kPerWarp, n - warp_first);  // particles of this warp (<= 0: none)
+    X += warp_first, Y += warp_first;
+    const unsigned int pitch = (unsigned int)g.pitch;
+    unsigned int f_cx = (unsigned int)(cx0 + lane) % pitch;                     // column / tail index of the lane's particle
+    unsigned int f_tail = (unsigned int)(row0 + (cx0 + lane) / (int)pitch) * (unsigned int)g.nx + f_cx;  // in the NEXT fetch
+
+    constexpr uint32_t kV = 1u << 24, kH = 1u << 25;
+    struct Trip {
+        T x, y, xu, yu, xl0, yl0;  // own position, the particle above, the particle left of lane 0's
+        uint32_t fl3;              // flag bytes: own | above << 8 | left << 16; kV / kH = the lane lists that stick
+        unsigned int tail;         // index of the particle in the (unpadded) cloth
+    };
+    auto fetch = [&](int trip) -> Trip {
+        Trip t;
+        t.x = t.y = t.xu = t.yu = t.xl0 = t.yl0 = T(0);
+        t.fl3 = 0u, t.tail = f_tail;
+        const int li = trip * 32 + lane;
+        if (li < n_here) {
+            const uint32_t f = s_f[w][16 + li];
+            t.fl3 = f;
             if (f & CLOTHGPU_FLAG_ACTIVE) {
-                if (g.own_row0 + ly > g.held_row0) fu = P.fl[base + i - g.pitch];
-                if (cx > 0) fw = P.fl[base + i - 1];
-                v = (fu & CLOTHGPU_FLAG_ALIVE_V) && (fu & CLOTHGPU_FLAG_ACTIVE);
-                h = (fw & CLOTHGPU_FLAG_ALIVE_H) && (fw & CLOTHGPU_FLAG_ACTIVE);
+                const uint32_t fu = s_fu[w][li], fw = f_cx > 0 ? s_f[w][15 + li] : 0u;
+                t.fl3 |= (fu << 8) | (fw << 16);
+                if ((fu & (CLOTHGPU_FLAG_ALIVE_V | CLOTHGPU_FLAG_ACTIVE)) == (CLOTHGPU_FLAG_ALIVE_V | CLOTHGPU_FLAG_ACTIVE)) t.fl3 |= kV;
+                if ((fw & (CLOTHGPU_FLAG_ALIVE_H | CLOTHGPU_FLAG_ACTIVE)) == (CLOTHGPU_FLAG_ALIVE_H | CLOTHGPU_FLAG_ACTIVE)) t.fl3 |= kH;
             }
+            // every lane loads its own position (its right neighbour may need it as the head of a horizontal stick)
+            t.x = X[li], t.y = Y[li];
+            if (t.fl3 & kV) t.xu = X[li - (int)pitch], t.yu = Y[li - (int)pitch];
+            if (lane == 0 && (t.fl3 & kH)) t.xl0 = X[li - 1], t.yl0 = Y[li - 1];
         }
-        // warp-ballot ranking: within a warp, lane l's sticks come after all sticks of lanes < l
+        // the lane's particle of the next trip: 32 further on, rows are `pitch` apart and hold nx particles
+        f_cx += 32, f_tail += 32;
+        while (f_cx >= pitch) f_cx -= pitch, f_tail += (unsigned int)g.nx - pitch;
+        return t;
+    };
+
+    Trip cur = fetch(0);
+#pragma unroll 1
+    for (int trip = 0; trip < kTrips; ++trip) {
+        if (trip * 32 >= n_here) break;  // warp-uniform
+        Trip nxt = cur;
+        if (trip + 1 < kTrips) nxt = fetch(trip + 1);  // its loads are in flight while this trip is written out
+        const bool v = (cur.fl3 & kV) != 0, h = (cur.fl3 & kH) != 0;
         const uint32_t bv = __ballot_sync(0xffffffffu, v), bh = __ballot_sync(0xffffffffu, h);
-        const unsigned int rank = __popc(bv & below) + __popc(bh & below);
-        if (lane == 0) warp_base[w] = __popc(bv) + __popc(bh);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int acc = 0;
-            for (int k = 0; k < kStreamThreads / 32; k++) {
-                const unsigned int t = warp_base[k];
-                warp_base[k] = acc;
-                acc += t;
-            }
-            warp_base[kStreamThreads / 32] = acc;
-        }
-        __syncthreads();
-        unsigned long long o = run + warp_base[w] + rank;
-        run += warp_base[kStreamThreads / 32];
-        if (v || h) {
-            const long long at = base + i;
-            const float x2 = (float)P.x[at], y2 = (float)P.y[at];  // cloth.go:110-111: float32(c.p2.x)
-            const bool hl2 = (f & CLOTHGPU_FLAG_HIGHLIGHT) != 0;
-            const unsigned int tail_i = (unsigned int)((long long)ly * g.nx + cx);
+        const unsigned int total = __popc(bv) + __popc(bh);
+        if (total) {  // warp-uniform
+            const float x2 = (float)cur.x, y2 = (float)cur.y;  // cloth.go:110-111: float32(c.p2.x)
+            // head of the horizontal stick = the lane to the left (lane 0: loaded separately)
+            float xl = __shfl_up_sync(0xffffffffu, x2, 1), yl = __shfl_up_sync(0xffffffffu, y2, 1);
+            if (lane == 0) xl = (float)cur.xl0, yl = (float)cur.yl0;
+            unsigned int r = __popc(bv & below) + __popc(bh & below);  // lane l's sticks come after those of lanes < l
+            const uint32_t hl_own = cur.fl3 & CLOTHGPU_FLAG_HIGHLIGHT;
             if (v) {
-                if (o < cap) {
-                    xyxy[o] = make_float4((float)P.x[at - g.pitch], (float)P.y[at - g.pitch], x2, y2);
-                    hl[o] = hl2 && (fu & CLOTHGPU_FLAG_HIGHLIGHT);  // cloth.go:127-128
-                    if (idx) idx[o] = make_uint2(tail_i - g.nx, tail_i);
+                s_xy[w][r] = make_float4((float)cur.xu, (float)cur.yu, x2, y2);
+                s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 8)) != 0;  // cloth.go:127-128: both ends highlighted
+                s_idx[w][r] = make_uint2(cur.tail - g.nx, cur.tail);
+                ++r;
+            }
+            if (h) {
+                s_xy[w][r] = make_float4(xl, yl, x2, y2);
+                s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 16)) != 0;
+                s_idx[w][r] = make_uint2(cur.tail - 1, cur.tail);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const unsigned int j = q * 32 + lane, o = run + j;
+                if (j < total && o < cap32) {
+                    xyxy[o] = s_xy[w][j];
+                    if (idx) idx[o] = s_idx[w][j];
                 }
-                o++;
             }
-            if (h && o < cap) {
-                xyxy[o] = make_float4((float)P.x[at - 1], (float)P.y[at - 1], x2, y2);
-                hl[o] = hl2 && (fw & CLOTHGPU_FLAG_HIGHLIGHT);
-                if (idx) idx[o] = make_uint2(tail_i - 1, tail_i);
-            }
+            __syncwarp();  // the staging buffer is rewritten by the next trip
+            run += total, hl_at += total;
         }
-        __syncthreads();  // warp_base is rewritten by the next sub-tile
+        cur = nxt;
+    }
+    // ---- highlight bytes [run0, run) of this warp: whole 16-byte groups as one store, the ragged ends byte by byte ----
+    __syncwarp();
+    const unsigned int first16 = run0 - hl_shift;  // 16-aligned output position of s_hl[w][0]
+    for (unsigned int c = lane * 16u; c < hl_at; c += 32u * 16u) {
+        const unsigned int o = first16 + c;
+        if (c >= hl_shift && c + 16u <= hl_at && o + 16u <= cap32) {
+            *reinterpret_cast<uint4*>(hl + o) = *reinterpret_cast<const uint4*>(&s_hl[w][c]);
+        } else {
+            for (unsigned int b = 0; b < 16u; ++b)
+                if (c + b >= hl_shift && c + b < hl_at && o + b < cap32) hl[o + b] = s_hl[w][c + b];
+        }
     }
 }
 

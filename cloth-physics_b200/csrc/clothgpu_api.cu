@@ -976,6 +976,8 @@ int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, size_t* max_stick
     }
     const size_t per = sizeof(float4) + sizeof(uint2) + 1;
     const size_t max_sticks = (size_t)2 * n;
+    if (max_sticks > 0xffffffffull)  // the scan and the scatter kernel keep output positions in 32 bits
+        return fail(CLOTHGPU_ERR_INVALID, "live-stick compaction supports cloths of up to 2^31 particles");
     if (c->seg_out_cap < max_sticks) {
         cudaFree(c->seg_out);
         c->seg_out = nullptr;
