@@ -304,6 +304,39 @@ def test_full_size_1024_fused_equals_streaming_and_oracle(oracle):
     assert gf.counters()["relaxations"] == 46 * 8 * (2 * 1024 * 1024 - 2048)
 
 
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("nx,ny,ens", [(1300, 900, 1), (515, 2051, 2), (260, 4400, 1)])
+def test_wavefront_schedule_equals_streaming_on_many_chunk_shapes(K, nx, ny, ens):
+    """The wavefront kernel's worker sets run up to one step apart (set-local barriers chained by producer/consumer
+    barriers, csrc/cloth_wave.cuh).  Shapes with several bands, several row chunks per band column and spans that run over
+    the end of a band column, every sweep count (the stage split between the sets depends on it), random jitter with
+    tears, pins and holes: the state after 12 frames must equal the one-launch-per-colour streaming schedule bit for bit.
+    (GPU against GPU: two independent implementations; the oracle pins both on the smaller shapes above.)"""
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=K, ensemble=ens)
+    gw, gs = clothgpu.Cloth(desc), clothgpu.Cloth(desc)
+    gw.set_schedule(SCHED_WAVE)
+    gs.set_schedule(SCHED_STREAMING)
+    for e in range(ens):
+        st = random_state(nx, ny, seed=K * 31 + nx + e)
+        gw.write_state(*st, cloth=e)
+        gs.write_state(*st, cloth=e)
+    f = _abi.default_frame(K)
+    f.win_w, f.win_h = 128 + 6 * nx + 50, 164 + 6 * ny + 20
+    f.buttons = MOUSE_DRAGGING
+    f.tear_length = 9.5
+    f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 128.0 + 3 * nx, 164.0 + 3 * ny, 120.0 + 3 * nx, 170.0 + 3 * ny
+    for t in range(12):
+        gw.step(f)
+        gs.step(f)
+    for e in range(ens):
+        assert_same_state(gw.read_state(cloth=e), gs.read_state(cloth=e), f"{nx}x{ny} K={K} cloth {e}: wave vs streaming")
+    cw, cs = gw.counters(), gs.counters()
+    for key in ("relaxations", "torn_last", "live_sticks", "alive_sticks", "pinned", "inactive"):
+        assert cw[key] == cs[key], key
+    gw.close()
+    gs.close()
+
+
 @pytest.mark.parametrize("K,schedule", [(1, SCHED_FUSED), (1, SCHED_ROWSTREAM), (3, SCHED_FUSED), (3, SCHED_WAVE),
                                         (8, SCHED_WAVE), (11, SCHED_FUSED)])
 def test_attached_strips_exchange_inside_the_frame_kernel(oracle, K, schedule):
