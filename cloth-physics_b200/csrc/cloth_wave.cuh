@@ -31,7 +31,10 @@
 namespace clothgpu_impl {
 
 constexpr int kWaveTW = 256, kWaveHW = 128;
-constexpr int kWaveWorkers = 512, kWaveEntry = 128, kWaveThreads = kWaveWorkers + kWaveEntry;
+#ifndef WAVE_WORKERS
+#define WAVE_WORKERS 512
+#endif
+constexpr int kWaveWorkers = WAVE_WORKERS, kWaveEntry = 128, kWaveThreads = kWaveWorkers + kWaveEntry;  // (384 workers: experiments with K <= 6)
 constexpr int kWaveGroups = kWaveWorkers / 64;  // worker groups of 64 column pairs
 #ifndef WAVE_SETS
 #define WAVE_SETS 2
@@ -47,6 +50,7 @@ constexpr int kWaveSets = WAVE_SETS;
 constexpr bool kWaveStagger = WAVE_STAGGER != 0;  // Y may start step s only after X's alpha phase of step s
 constexpr int kBarEntry = 1, kBarX = 2, kBarY = 3, kBarXDone = 4 /* .. 7 */, kBarYDone = 8 /* .. 11 */;
 constexpr int kWaveSetThreads = kWaveWorkers / 2;
+static_assert(kWaveSets == 1 || kWaveWorkers == 512, "the two-set stage mapping is written for 8 worker groups");
 
 #ifdef WAVE_ABLATE_BAR  // timing experiment only (results are wrong): what do the barriers cost?
 __device__ __forceinline__ void bar_sync(int, int) {}

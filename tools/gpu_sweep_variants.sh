@@ -9,7 +9,7 @@ for v in $1; do
     timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$3" 2>&1 | tail -2 | tr '\n' ' '; echo " [$v parity]"
   fi
   for wl in $2; do
-    timeout 300 python bench.py --workload $wl --steps 60 --warmup 10 --no-cpu > gpurun_out/var_${v}_${wl}.json 2> gpurun_out/var_${v}_${wl}.err
+    timeout 300 python bench.py --workload $wl --steps 60 --warmup 10 --no-cpu ${BENCH_ARGS:-} > gpurun_out/var_${v}_${wl}.json 2> gpurun_out/var_${v}_${wl}.err
     python - gpurun_out/var_${v}_${wl}.json $v $wl <<'PY'
 import json,sys
 try:
