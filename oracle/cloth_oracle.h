@@ -7,7 +7,9 @@
  *
  * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and it cannot be built here
  * (no Go toolchain, Gio not vendored), so this restatement is pinned only by known-answer tests derived
- * from the reference's source text (tests/test_oracle_kat.py) — not by outputs of the reference itself.
+ * from the reference's source text and by bit-for-bit agreement with a second, independent restatement (a
+ * line-by-line Python transliteration of the Go files that keeps their data structures and slice semantics,
+ * tests/go_transliteration.py; both in tests/test_oracle_kat.py) — not by outputs of the reference itself.
  *
  * The only thing shared with the product is the POD input types of include/clothgpu.h
  * (clothgpu_desc / clothgpu_frame and the CLOTHGPU_FLAG_* bit layout), so one harness drives both.

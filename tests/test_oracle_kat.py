@@ -329,3 +329,98 @@ def test_colour_vs_sequential_physical_tolerance(oracle):
     assert worst_rms <= 0.75             # in units of the stick rest length
     assert worst_strain > 0 and worst_rms > 0   # the two orders are genuinely different computations
     assert a.relaxations == b.relaxations       # same sticks visited (no tearing without a drag)
+
+
+def _transliteration_cloth(desc, frames_fn):
+    """The Go transliteration (tests/go_transliteration.py) set up like main.go:149-166 for a descriptor."""
+    import go_transliteration as gt
+    f0 = frames_fn(0)
+    hud = gt.Hud([float(v) for v in f0.slider], float(f0.drag_force_max))
+    cloth = gt.Cloth(desc.width, desc.height, desc.spacing)
+    cloth.Init(desc.pos_x, desc.pos_y, hud)
+    return gt, hud, cloth
+
+
+def _transliteration_step(gt, hud, cloth, mouse, f):
+    from clothgpu._abi import MOUSE_CTRL, MOUSE_DRAGGING, MOUSE_LEFT, MOUSE_RIGHT
+    for i in range(5):
+        hud.Sliders[i].Value = gt.f32(float(f.slider[i]))
+    hud.Sliders[gt.HudSliderDragForce].Max = gt.f32(float(f.drag_force_max))
+    hud.WinOffsetX, hud.WinOffsetY = f.win_off_x, f.win_off_y
+    mouse.x, mouse.y, mouse.px, mouse.py, mouse.force = f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py, f.mouse_force
+    mouse.scrollY = gt.f32(float(f.scroll_y))
+    mouse.leftDown, mouse.rightDown = bool(f.buttons & MOUSE_LEFT), bool(f.buttons & MOUSE_RIGHT)
+    mouse.isDragging, mouse.ctrlDown = bool(f.buttons & MOUSE_DRAGGING), bool(f.buttons & MOUSE_CTRL)
+    return cloth.Update(f.win_w, f.win_h, mouse, hud, f.dt)
+
+
+def _assert_oracle_equals_transliteration(o, cloth, what):
+    from clothgpu._abi import FLAG_ACTIVE, FLAG_HIGHLIGHT, FLAG_PIN
+    x, y, px, py, fl = o.read_state()
+    ps = cloth.particles
+    for name, got, want in (("x", x, [p.x for p in ps]), ("y", y, [p.y for p in ps]),
+                            ("px", px, [p.px for p in ps]), ("py", py, [p.py for p in ps])):
+        want = np.array(want, np.float64)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"{what}: {name} differs at " \
+            f"{np.flatnonzero(got != want)[:5]}"
+    bits = np.array([(FLAG_PIN if p.pinX else 0) | (FLAG_ACTIVE if p.isActive else 0) |
+                     (FLAG_HIGHLIGHT if p.highlighted else 0) for p in ps], np.uint8)
+    assert np.array_equal(fl & (FLAG_PIN | FLAG_ACTIVE | FLAG_HIGHLIGHT), bits), f"{what}: pin/active/highlight bits"
+    assert o.slice_len == cloth.constraints_len, f"{what}: len(cloth.constraints)"
+
+
+def test_oracle_equals_line_by_line_go_transliteration_on_the_default_trace(oracle):
+    """Two independent restatements of the reference must agree bit for bit: the C oracle in its sequential-faithful
+    mode, and a literal Python transliteration of physics/{cloth,particle,constraint}.go that keeps the Go data
+    structures and slice semantics (tests/go_transliteration.py).  BASELINE configs[0]: default 171 x 36 cloth, scripted
+    trace (ctrl-pin, slow drag with the force ramp, hole punch, scroll, fast zig-zag drag with tearing), every 25th frame
+    and the last one compared, plus the visit count of every frame."""
+    from traces import c0_trace
+    from clothgpu import _abi
+    import go_transliteration as gt
+    n_frames = 820
+    frames = c0_trace(n_frames)
+    desc = _abi.grid_desc(171, 36, pin_rule=_abi.PIN_REFERENCE)
+    o = oracle.OracleCloth(desc, oracle.SEQ_FAITHFUL)
+    gt_, hud, cloth = _transliteration_cloth(desc, lambda i: frames[i])
+    mouse = gt.Mouse()
+    torn_frames = 0
+    for t, f in enumerate(frames):
+        before = o.relaxations
+        o.step(f)
+        visited = _transliteration_step(gt, hud, cloth, mouse, f)
+        assert o.relaxations - before == visited, f"frame {t}: stick visits"
+        torn_frames += o.torn_last > 0
+        if t % 25 == 0 or t == n_frames - 1 or o.torn_last:
+            _assert_oracle_equals_transliteration(o, cloth, f"frame {t}")
+    assert torn_frames > 0 and cloth.constraints_len < 2 * 171 * 36 - 171 - 36  # the trace did tear sticks
+    assert any(not p.isActive for p in cloth.particles) and sum(p.pinX for p in cloth.particles) > 11
+
+
+def test_oracle_equals_go_transliteration_under_mass_tearing(oracle):
+    """The slice-removal artefact (constraint.go:57-64 under cloth.go:96) at scale: a low tear threshold makes dozens of
+    sticks tear per frame, so skipped successors and the re-visited stale tail decide the result."""
+    from clothgpu import _abi
+    import go_transliteration as gt
+    desc = _abi.grid_desc(41, 23, pin_rule=_abi.PIN_REFERENCE)
+    o = oracle.OracleCloth(desc, oracle.SEQ_FAITHFUL)
+    f = _abi.default_frame(1)
+    f.buttons = _abi.MOUSE_DRAGGING | _abi.MOUSE_LEFT
+    f.tear_length = 6.4
+    f.mouse_force = 0.7
+    gt_, hud, cloth = _transliteration_cloth(desc, lambda i: f)
+    mouse = gt.Mouse()
+    total_torn = 0
+    for t in range(60):
+        f.mouse_px, f.mouse_py = 128.0 + 4 * t, 164.0 + 2 * t
+        f.mouse_x, f.mouse_y = f.mouse_px + 9.0, f.mouse_py + 5.0
+        before = o.relaxations
+        o.step(f)
+        # constraint_update takes the frame's threshold where the Go source has the literal 150
+        gt.constraint_update.__defaults__ = (f.tear_length, f.relax_gain)
+        visited = _transliteration_step(gt, hud, cloth, mouse, f)
+        assert o.relaxations - before == visited, f"frame {t}: stick visits"
+        total_torn += o.torn_last
+        _assert_oracle_equals_transliteration(o, cloth, f"frame {t}")
+    gt.constraint_update.__defaults__ = (150, 0.35)
+    assert total_torn > 100
