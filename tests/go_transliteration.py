@@ -76,6 +76,8 @@ class Cloth:
         self.constraints_arr = []
         self.constraints_len = 0
         self.isInitialized = False
+        self.colour_of = {}   # not in the Go code: which colour class a stick falls in (UpdateColourOrdered only)
+        self.creation = None
 
     def Init(self, posX, posY, hud):  # physics/cloth.go:42-81
         clothX = self.Width // self.spacing
@@ -91,14 +93,17 @@ class Cloth:
                 if y != 0:
                     top = self.particles[x + (y - 1) * (clothX + 1)]
                     self.constraints_arr.append(Constraint(top, particle, float(self.spacing)))
+                    self.colour_of[id(self.constraints_arr[-1])] = 2 + ((y - 1) & 1)  # vertical, head row y-1
                 if x != 0:
                     left = self.particles[len(self.particles) - 1]
                     self.constraints_arr.append(Constraint(left, particle, float(self.spacing)))
+                    self.colour_of[id(self.constraints_arr[-1])] = (x - 1) & 1        # horizontal, head column x-1
                 pinX = x % (clothX // 10)  # ZeroDivisionError where Go panics (clothX < 10)
                 if y == 0 and pinX == 0:
                     particle.pinX = True
                 self.particles.append(particle)
         self.constraints_len = len(self.constraints_arr)
+        self.creation = list(self.constraints_arr)
         self.isInitialized = True
 
     def Update(self, width, height, mouse, hud, dt):  # physics/cloth.go:85-100 (physics half)
@@ -113,6 +118,22 @@ class Cloth:
             if c.p1.isActive and c.p2.isActive:
                 constraint_update(c, self, mouse)
                 visited += 1
+        return visited
+
+    def UpdateColourOrdered(self, width, height, mouse, hud, dt, iterations):
+        """BASELINE.json's deterministic mode: the SAME Go functions, fed the colour-ordered stick sequence — H-even, H-odd,
+        V-even, V-odd (by the parity of the head particle's column / row), `iterations` times — instead of creation order.
+        A stick is visited while it is still in cloth.constraints and both ends are active (cloth.go:97)."""
+        for p in self.particles:
+            particle_update(p, width, height, mouse, hud, dt)
+        visited = 0
+        for _ in range(iterations):
+            for colour in range(4):
+                in_slice = {id(c) for c in self.constraints_arr[:self.constraints_len]}
+                for c in self.creation:
+                    if self.colour_of[id(c)] == colour and id(c) in in_slice and c.p1.isActive and c.p2.isActive:
+                        constraint_update(c, self, mouse)
+                        visited += 1
         return visited
 
 

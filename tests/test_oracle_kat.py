@@ -424,3 +424,51 @@ def test_oracle_equals_go_transliteration_under_mass_tearing(oracle):
         _assert_oracle_equals_transliteration(o, cloth, f"frame {t}")
     gt.constraint_update.__defaults__ = (150, 0.35)
     assert total_torn > 100
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_colour_mode_equals_go_transliteration_fed_the_colour_ordered_sequence(oracle, K):
+    """The mode the GPU must match bit for bit (oracle.COLOUR) against the transliterated Go functions fed the
+    colour-ordered stick sequence (BASELINE.json's deterministic mode), on the part of the default trace that pins,
+    drags, punches holes and tears."""
+    from traces import c0_trace
+    from clothgpu import _abi
+    import go_transliteration as gt
+    frames = c0_trace(700, iterations=K)
+    desc = _abi.grid_desc(171, 36, pin_rule=_abi.PIN_REFERENCE)
+    o = oracle.OracleCloth(desc, oracle.COLOUR)
+    gt_, hud, cloth = _transliteration_cloth(desc, lambda i: frames[i])
+    mouse = gt.Mouse()
+    step = 1 if K == 1 else 2  # (the pure-Python loop is slow: K = 3 replays every second frame of the trace)
+    torn = 0
+    for t in range(0, 700, step):
+        f = frames[t]
+        before = o.relaxations
+        o.step(f)
+        real_update = cloth.Update
+        cloth.Update = lambda w, h, m, hd, dt: cloth.UpdateColourOrdered(w, h, m, hd, dt, K)
+        visited = _transliteration_step(gt, hud, cloth, mouse, f)
+        cloth.Update = real_update
+        assert o.relaxations - before == visited, f"frame {t}: stick visits"
+        torn += o.torn_last
+        if t % 20 == 0 or o.torn_last or t + step >= 700:
+            _assert_oracle_equals_transliteration_masked(o, cloth, f"K={K} frame {t}")
+    assert torn > 0
+
+
+def _assert_oracle_equals_transliteration_masked(o, cloth, what):
+    """Like _assert_oracle_equals_transliteration, for the masked modes: the oracle keeps an alive bit per stick instead
+    of a slice, so the slice length is compared with the number of alive bits."""
+    from clothgpu._abi import FLAG_ACTIVE, FLAG_ALIVE_H, FLAG_ALIVE_V, FLAG_HIGHLIGHT, FLAG_PIN
+    x, y, px, py, fl = o.read_state()
+    ps = cloth.particles
+    for name, got, want in (("x", x, [p.x for p in ps]), ("y", y, [p.y for p in ps]),
+                            ("px", px, [p.px for p in ps]), ("py", py, [p.py for p in ps])):
+        want = np.array(want, np.float64)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"{what}: {name} differs at " \
+            f"{np.flatnonzero(got != want)[:5]}"
+    bits = np.array([(FLAG_PIN if p.pinX else 0) | (FLAG_ACTIVE if p.isActive else 0) |
+                     (FLAG_HIGHLIGHT if p.highlighted else 0) for p in ps], np.uint8)
+    assert np.array_equal(fl & (FLAG_PIN | FLAG_ACTIVE | FLAG_HIGHLIGHT), bits), f"{what}: pin/active/highlight bits"
+    alive = int(np.count_nonzero(fl & FLAG_ALIVE_H) + np.count_nonzero(fl & FLAG_ALIVE_V))
+    assert alive == cloth.constraints_len, f"{what}: alive sticks vs len(cloth.constraints)"
