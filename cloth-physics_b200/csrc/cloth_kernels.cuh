@@ -488,6 +488,39 @@ __global__ void __launch_bounds__(kStreamThreads)
     }
 }
 
+// addSegment / normal of the reference's render loops (physics/cloth.go:150-168) on the compacted live-stick list: for every
+// stick the four float32 corners {a+n, b+n, b-n, a-n} of its outline quad, n = the stick's normal scaled to the line
+// width.  math.Hypot is max * sqrt(1 + (min/max)^2) in binary64 (hypot_amd64.s); everything else is float32 arithmetic,
+// one rounding per operation (-fmad=false, IEEE division).  One thread per stick: 16 bytes in, 32 bytes out.
+__global__ void __launch_bounds__(kStreamThreads)
+    segment_quads_kernel(const float4* __restrict__ xyxy, const unsigned long long* __restrict__ total, float line_width,
+                         float4* __restrict__ quads, unsigned long long cap) {
+    const unsigned long long n = min(*total, cap);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float4 s = xyxy[i];  // a = (s.x, s.y), b = (s.z, s.w)
+        const float dx = s.z - s.x, dy = s.w - s.y;  // dir := b.Sub(a)
+        const float rx = +dy, ry = -dx;              // dir.X, dir.Y = +dir.Y, -dir.X
+        double p = fabs((double)rx), q = fabs((double)ry);
+        if (p < q) {
+            const double t = p;
+            p = q, q = t;
+        }
+        double d = 0.0;
+        if (p != 0.0) {
+            q = q / p;
+            d = p * sqrt(1.0 + q * q);
+        }
+        float nx = 0.f, ny = 0.f;  // f32.Point{} when |d| < 1e-5
+        if (!(fabs(d) < 1e-5)) {
+            const float sc = line_width / (float)d;
+            nx = rx * sc, ny = ry * sc;
+        }
+        quads[2 * i] = make_float4(s.x + nx, s.y + ny, s.z + nx, s.w + ny);
+        quads[2 * i + 1] = make_float4(s.z - nx, s.w - ny, s.x - nx, s.y - ny);
+    }
+}
+
 // ---- row strips over several GPUs: stream-ordered handshake and the explicit edge-row push -----------------------
 // Every strip owns two 32-bit epoch slots in its own memory: slot 0 is written by its upper neighbour, slot 1 by
 // its lower neighbour.  Operation k of a strip (a fused launch, or a push) may start once both neighbours have

@@ -112,6 +112,8 @@ struct clothgpu {
     void* seg_out = nullptr;
     size_t seg_out_cap = 0;
     unsigned long long* seg_total = nullptr;
+    void* seg_quads = nullptr;  // 2 float4 per stick, allocated on the first clothgpu_read_quads_f32
+    size_t seg_quads_cap = 0;
 };
 
 namespace {
@@ -575,6 +577,7 @@ void free_all(clothgpu* c) {
     cudaFree(c->seg_counts);
     cudaFree(c->seg_out);
     cudaFree(c->seg_total);
+    cudaFree(c->seg_quads);
     if (c->frames_copied) cudaEventDestroy(c->frames_copied);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1030,6 +1033,43 @@ int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t*
         if (xyxy) CU_TRY(cudaMemcpy(xyxy, d_xyxy, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost));
         if (highlighted) CU_TRY(cudaMemcpy(highlighted, d_hl, (size_t)total, cudaMemcpyDeviceToHost));
         if (sticks_idx) CU_TRY(cudaMemcpy(sticks_idx, d_idx, (size_t)total * sizeof(uint2), cudaMemcpyDeviceToHost));
+    }
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float* quads, uint8_t* highlighted,
+                            size_t cap, size_t* n_out) {
+    if (int rc = check_handle(c)) return rc;
+    if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
+    if (!(line_width >= 0.f) || !(line_width <= 1e30f)) return fail(CLOTHGPU_ERR_INVALID, "line width must be finite and >= 0");
+    size_t max_sticks = 0;
+    if (int rc = compact_enqueue(c, cloth, false, &max_sticks)) return rc;
+    float4* d_xyxy = (float4*)c->seg_out;
+    uint8_t* d_hl = (uint8_t*)((uint2*)(d_xyxy + max_sticks) + max_sticks);
+    if (quads) {
+        if (c->seg_quads_cap < max_sticks) {
+            cudaFree(c->seg_quads);
+            c->seg_quads = nullptr;
+            c->seg_quads_cap = 0;
+            CU_TRY(cudaMalloc(&c->seg_quads, max_sticks * 2 * sizeof(float4)));
+            c->seg_quads_cap = max_sticks;
+        }
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((max_sticks + kStreamThreads - 1) / kStreamThreads,
+                                                                             (size_t)c->sm_count * 16));
+        segment_quads_kernel<<<grid, kStreamThreads, 0, c->stream>>>(d_xyxy, c->seg_total, line_width, (float4*)c->seg_quads,
+                                                                      (unsigned long long)max_sticks);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    unsigned long long total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, c->seg_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *n_out = (size_t)total;
+    if (!quads && !highlighted) return CLOTHGPU_OK;  // count only
+    if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
+    if (total) {
+        if (quads) CU_TRY(cudaMemcpy(quads, c->seg_quads, (size_t)total * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
+        if (highlighted) CU_TRY(cudaMemcpy(highlighted, d_hl, (size_t)total, cudaMemcpyDeviceToHost));
     }
     return CLOTHGPU_OK;
 }

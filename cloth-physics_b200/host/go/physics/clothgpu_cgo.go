@@ -27,7 +27,6 @@ import "C"
 import (
 	"fmt"
 	"image/color"
-	"math"
 	"runtime"
 	"unsafe"
 
@@ -51,7 +50,7 @@ type Cloth struct {
 	tint    color.NRGBA
 	gpu     *C.clothgpu
 	// host staging for the render export, reused across frames
-	segs []float32
+	quads []float32
 	hl   []uint8
 }
 
@@ -125,45 +124,40 @@ func (c *Cloth) Update(gtx layout.Context, mouse *Mouse, hud *gui.Hud, dt float6
 	f.iterations = 1 // the reference relaxes once per frame (cloth.go:96-100)
 	c.check(C.clothgpu_step(c.gpu, &f))
 
-	// render half, cloth.go:102-138
+	// render half, cloth.go:102-138: the device applies addSegment / normal (cloth.go:150-168) to every live stick and
+	// hands back the four corners of its outline quad, in the order the two loops of cloth.go:108-114 / 126-134 walk
 	var info C.clothgpu_info
 	C.clothgpu_get_info(c.gpu, &info)
 	capSticks := int(info.sticks)
-	if cap(c.segs) < 4*capSticks {
-		c.segs = make([]float32, 4*capSticks)
+	if cap(c.quads) < 8*capSticks {
+		c.quads = make([]float32, 8*capSticks)
 		c.hl = make([]uint8, capSticks)
 	}
 	var n C.size_t
-	c.check(C.clothgpu_read_segments_f32(c.gpu, 0, (*C.float)(unsafe.Pointer(&c.segs[0])),
-		(*C.uint8_t)(unsafe.Pointer(&c.hl[0])), nil, C.size_t(capSticks), &n))
+	c.check(C.clothgpu_read_quads_f32(c.gpu, 0, C.float(strokeWidth), (*C.float)(unsafe.Pointer(&c.quads[0])),
+		(*C.uint8_t)(unsafe.Pointer(&c.hl[0])), C.size_t(capSticks), &n))
 
 	var path clip.Path
 	path.Begin(gtx.Ops)
 	for i := 0; i < int(n); i++ {
-		quad(&path, f32.Pt(c.segs[4*i], c.segs[4*i+1]), f32.Pt(c.segs[4*i+2], c.segs[4*i+3]), strokeWidth)
+		outline(&path, c.quads[8*i:8*i+8])
 	}
 	paint.FillShape(gtx.Ops, c.tint, clip.Outline{Path: path.End()}.Op())
 	path.Begin(gtx.Ops)
 	for i := 0; i < int(n); i++ {
 		if c.hl[i] != 0 {
-			quad(&path, f32.Pt(c.segs[4*i], c.segs[4*i+1]), f32.Pt(c.segs[4*i+2], c.segs[4*i+3]), strokeWidth)
+			outline(&path, c.quads[8*i:8*i+8])
 		}
 	}
 	paint.FillShape(gtx.Ops, color.NRGBA{R: c.tint.R, A: c.tint.A}, clip.Outline{Path: path.End()}.Op())
 }
 
-// quad emits the stroke outline of one stick (cloth.go:150-168 does the same with a unit normal).
-func quad(p *clip.Path, a, b f32.Point, w float32) {
-	d := b.Sub(a)
-	l := float32(math.Hypot(float64(d.X), float64(d.Y)))
-	if l == 0 {
-		return
-	}
-	n := f32.Pt(-d.Y*w/l, d.X*w/l)
-	p.MoveTo(a.Add(n))
-	p.LineTo(b.Add(n))
-	p.LineTo(b.Sub(n))
-	p.LineTo(a.Sub(n))
+// outline adds one stick's quad {a+n, b+n, b-n, a-n} to the path, as addSegment does (cloth.go:150-157).
+func outline(p *clip.Path, q []float32) {
+	p.MoveTo(f32.Pt(q[0], q[1]))
+	p.LineTo(f32.Pt(q[2], q[3]))
+	p.LineTo(f32.Pt(q[4], q[5]))
+	p.LineTo(f32.Pt(q[6], q[7]))
 	p.Close()
 }
 

@@ -153,6 +153,20 @@ class Cloth {
         return n;
     }
 
+    // the same loops one step further: addSegment / normal (physics/cloth.go:150-168) applied on the device; out gets 8
+    // floats per live stick {a+n, b+n, b-n, a-n}
+    size_t Quads(std::vector<float>& out, std::vector<uint8_t>& highlighted, float lineWidth = 0.6f) {
+        clothgpu_info info;
+        Check(clothgpu_get_info(gpu_, &info), "Quads");
+        out.resize((size_t)info.sticks * 8);
+        highlighted.resize((size_t)info.sticks);
+        size_t n = 0;
+        Check(clothgpu_read_quads_f32(gpu_, 0, lineWidth, out.data(), highlighted.data(), (size_t)info.sticks, &n), "Quads");
+        out.resize(n * 8);
+        highlighted.resize(n);
+        return n;
+    }
+
     clothgpu_counters Counters() {
         clothgpu_counters c;
         Check(clothgpu_get_counters(gpu_, &c), "Counters");

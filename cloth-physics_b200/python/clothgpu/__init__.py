@@ -21,7 +21,8 @@ EXPORTS = [
     "clothgpu_frame_default", "clothgpu_desc_default", "clothgpu_create", "clothgpu_reset",
     "clothgpu_destroy", "clothgpu_step", "clothgpu_step_n", "clothgpu_step_each", "clothgpu_sync",
     "clothgpu_get_info", "clothgpu_set_schedule", "clothgpu_read_state", "clothgpu_write_state",
-    "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_compact_segments", "clothgpu_get_counters",
+    "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_read_quads_f32", "clothgpu_compact_segments",
+    "clothgpu_get_counters",
     "clothgpu_halo_region", "clothgpu_strip_export", "clothgpu_strip_attach", "clothgpu_strip_push", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
     "clothgpu_last_error", "clothgpu_version",
 ]
@@ -62,6 +63,8 @@ def lib():
         L.clothgpu_read_masks.argtypes = [vp, C.c_int32, u32p, u32p, u32p, u32p, u32p]
         L.clothgpu_read_segments_f32.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), u8p, u32p,
                                                  C.c_size_t, C.POINTER(C.c_size_t)]
+        L.clothgpu_read_quads_f32.argtypes = [vp, C.c_int32, C.c_float, C.POINTER(C.c_float), u8p,
+                                              C.c_size_t, C.POINTER(C.c_size_t)]
         L.clothgpu_compact_segments.argtypes = [vp, C.c_int32]
         L.clothgpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.clothgpu_halo_region.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -182,6 +185,16 @@ class Cloth:
         if with_indices:
             return xyxy[:n.value], hl[:n.value], idx[:n.value]
         return xyxy[:n.value], hl[:n.value]
+
+    def read_quads(self, cloth=0, line_width=0.6):
+        """addSegment of every live stick (physics/cloth.go:150-157): (n, 8) float32 corners and the highlight bytes."""
+        cap = 2 * self.nx * self.rows
+        quads = np.empty((cap, 8), np.float32)
+        hl = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        _check(self._L.clothgpu_read_quads_f32(self._h, cloth, C.c_float(line_width), _p(quads, C.c_float),
+                                               _p(hl, C.c_uint8), cap, C.byref(n)))
+        return quads[:n.value], hl[:n.value]
 
     def compact_segments(self, cloth=0):
         """Device-side live-stick compaction only (asynchronous)."""

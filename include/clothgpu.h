@@ -231,6 +231,15 @@ CLOTHGPU_API int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, 
 CLOTHGPU_API int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
                                uint32_t* sticks_idx, size_t cap, size_t* n);
 
+/* The outline geometry the reference's render loops hand to Gio (physics/cloth.go:108-114 -> addSegment :150-157 ->
+ * normal :160-168): for every live stick, in the order of clothgpu_read_segments_f32, the four float32 corners
+ * {a+n, b+n, b-n, a-n} (8 floats: MoveTo, LineTo, LineTo, LineTo) where n is the stick's normal scaled to `line_width`
+ * (the reference's lineWidth is 0.6, physics/cloth.go:16; a stick shorter than 1e-5 gets n = 0 as in normal()).
+ * `highlighted` as in clothgpu_read_segments_f32 (the second render loop, :126-134, draws that subset).  `cap` = capacity
+ * in sticks; *n = live sticks; with both output pointers NULL only the count is returned. */
+CLOTHGPU_API int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float* quads,
+                            uint8_t* highlighted, size_t cap, size_t* n);
+
 /* Only the device half of the above: build the compacted live-stick list of cloth `cloth` in device memory,
  * asynchronously on the handle's stream (the next clothgpu_read_segments_f32 re-runs it; with all three output
  * pointers NULL that call returns just the count).  Lets a renderer that consumes the list on the GPU, or a benchmark

@@ -156,6 +156,36 @@ int64_t oracle_last_visit_order(const oracle_cloth* o, int64_t* ids, int64_t cap
     return o->n_visit;
 }
 
+/* math.Hypot as the amd64 assembly (and the portable Go version) computes it: max * sqrt(1 + (min/max)^2),
+ * finite arguments only. */
+static double go_hypot(double p, double q) {
+    p = fabs(p), q = fabs(q);
+    if (p < q) {
+        double t = p;
+        p = q, q = t;
+    }
+    if (p == 0) return 0;
+    q = q / p;
+    return p * sqrt(1 + q * q);
+}
+
+void oracle_segment_quad(const float* ab, float line_width, float* quad8) {
+    const float ax = ab[0], ay = ab[1], bx = ab[2], by = ab[3];
+    float dirx = bx - ax, diry = by - ay;            /* dir := b.Sub(a)                      cloth.go:161 */
+    const float rx = +diry, ry = -dirx;              /* dir.X, dir.Y = +dir.Y, -dir.X        :162 */
+    dirx = rx, diry = ry;
+    const double d = go_hypot((double)dirx, (double)diry);  /* :163 */
+    float nx = 0.0f, ny = 0.0f;                      /* f32.Point{} when |d| < 1e-5          :164-166 */
+    if (!(fabs(d) < 1e-5)) {
+        const float s = line_width / (float)d;       /* dir.Mul(w / float32(d))              :167 */
+        nx = dirx * s, ny = diry * s;
+    }
+    quad8[0] = ax + nx, quad8[1] = ay + ny;          /* p.MoveTo(a.Add(n))                   :152 */
+    quad8[2] = bx + nx, quad8[3] = by + ny;          /* p.LineTo(b.Add(n))                   :153 */
+    quad8[4] = bx - nx, quad8[5] = by - ny;          /* p.LineTo(b.Sub(n))                   :154 */
+    quad8[6] = ax - nx, quad8[7] = ay - ny;          /* p.LineTo(a.Sub(n))                   :155 */
+}
+
 int oracle_stick_update(double* x1, double* y1, double* x2, double* y2, int pin1, int pin2,
                         double length, int dragging, double tear_length, double relax_gain) {
     particle_f64 a = {0}, b = {0};

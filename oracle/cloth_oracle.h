@@ -77,6 +77,10 @@ int oracle_write_rows(oracle_cloth* c, int32_t row0, int32_t rows, const double*
  * looked at (before the isActive test), up to cap entries; returns the number of visits. */
 int64_t oracle_last_visit_order(const oracle_cloth* c, int64_t* ids, int64_t cap);
 
+/* addSegment (physics/cloth.go:150-157) with normal (:160-168): the four float32 corners {a+n, b+n, b-n, a-n} of the
+ * outline quad the reference's render loops emit for a stick with float32 endpoints ab = {ax, ay, bx, by}. */
+void oracle_segment_quad(const float* ab, float line_width, float* quad8);
+
 /* Stand-alone kernels for known-answer tests. */
 /* constraint.Update on one stick (physics/constraint.go:25-54).  Returns 1 if it tore. */
 int oracle_stick_update(double* x1, double* y1, double* x2, double* y2, int pin1, int pin2,

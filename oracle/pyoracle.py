@@ -54,6 +54,7 @@ def lib():
         L.oracle_last_visit_order.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int64]
         L.oracle_stick_update.argtypes = [dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_int,
                                           C.c_double, C.c_double]
+        L.oracle_segment_quad.argtypes = [C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -144,3 +145,14 @@ def stick_update(x1, y1, x2, y2, pin1=False, pin2=False, length=6.0, dragging=Fa
     tore = lib().oracle_stick_update(*[C.byref(a) for a in v], int(pin1), int(pin2), length,
                                      int(dragging), tear_length, relax_gain)
     return tuple(a.value for a in v), bool(tore)
+
+
+def segment_quads(xyxy, line_width=0.6):
+    """addSegment (physics/cloth.go:150-157) for an (n, 4) float32 array of stick endpoints -> (n, 8) float32 corners."""
+    xyxy = np.ascontiguousarray(xyxy, np.float32).reshape(-1, 4)
+    out = np.empty((len(xyxy), 8), np.float32)
+    L = lib()
+    for i in range(len(xyxy)):
+        L.oracle_segment_quad(xyxy[i].ctypes.data_as(C.POINTER(C.c_float)), line_width,
+                              out[i].ctypes.data_as(C.POINTER(C.c_float)))
+    return out

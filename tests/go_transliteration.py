@@ -231,3 +231,31 @@ def remove_constraint(c, cloth):  # physics/constraint.go:57-64
             arr[idx:n - 1] = arr[idx + 1:n]
             cloth.constraints_len = n - 1
             break
+
+
+# ---- the render half's geometry: addSegment / normal (physics/cloth.go:150-168), float32 arithmetic ------------------
+# A float32 +, -, *, / of float32 operands equals the binary64 result rounded to float32 (53 >= 2 * 24 + 2 bits).
+def go_hypot(p, q):  # math.Hypot: max * sqrt(1 + (min/max)^2) (src/math/hypot.go and hypot_amd64.s), finite arguments
+    p, q = abs(p), abs(q)
+    if p < q:
+        p, q = q, p
+    if p == 0:
+        return 0.0
+    q = q / p
+    return p * math.sqrt(1 + q * q)
+
+
+def normal(a, b, w):  # physics/cloth.go:160-168
+    dirx, diry = f32(b[0] - a[0]), f32(b[1] - a[1])
+    dirx, diry = +diry, -dirx
+    d = go_hypot(dirx, diry)
+    if abs(d) < 1e-5:
+        return (0.0, 0.0)
+    s = f32(w / f32(d))
+    return (f32(dirx * s), f32(diry * s))
+
+
+def add_segment(a, b, w):  # physics/cloth.go:150-157: MoveTo(a+n), LineTo(b+n), LineTo(b-n), LineTo(a-n)
+    n = normal(a, b, w)
+    return (f32(a[0] + n[0]), f32(a[1] + n[1]), f32(b[0] + n[0]), f32(b[1] + n[1]),
+            f32(b[0] - n[0]), f32(b[1] - n[1]), f32(a[0] - n[0]), f32(a[1] - n[1]))

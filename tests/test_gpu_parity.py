@@ -172,6 +172,30 @@ def test_live_stick_list_matches_reference_render_order(oracle):
     assert np.all(idx[:, 1] > idx[:, 0])
 
 
+def test_outline_quads_match_addsegment_of_the_reference(oracle):
+    """clothgpu_read_quads_f32 = addSegment / normal (physics/cloth.go:150-168) over the live-stick list: bit-exact float32
+    against the oracle's restatement on the state the scripted trace leaves (torn, punched, highlighted)."""
+    desc = _abi.default_desc()
+    g, o = make_pair(oracle, desc, SCHED_ROWSTREAM)
+    for t, f in enumerate(c0_trace(700)):
+        g.step(f)
+        o.step(f)
+    segs, seg_hl = g.read_segments()
+    quads, hl = g.read_quads(line_width=0.6)
+    assert quads.shape == (len(segs), 8) and np.array_equal(hl, seg_hl)
+    want = oracle.segment_quads(segs, 0.6)
+    assert np.array_equal(quads.view(np.uint32), want.view(np.uint32))
+    # a degenerate stick (both ends on the same spot) gets a zero normal, as normal() returns f32.Point{}
+    x, y, px, py, fl = g.read_state()
+    x[1], y[1] = x[0], y[0]
+    g.write_state(x, y, px, py, fl)
+    q2, _ = g.read_quads()
+    s2, _ = g.read_segments()
+    assert np.array_equal(q2.view(np.uint32), oracle.segment_quads(s2, 0.6).view(np.uint32))
+    k = int(np.flatnonzero((s2[:, 0] == s2[:, 2]) & (s2[:, 1] == s2[:, 3]))[0])
+    assert np.array_equal(q2[k], np.tile(s2[k, :2], 4))
+
+
 @pytest.mark.parametrize("K,schedule", [(8, SCHED_FUSED), (8, SCHED_WAVE), (1, SCHED_FUSED), (1, SCHED_ROWSTREAM)])
 def test_ensemble_cloths_are_independent(oracle, K, schedule):
     nx, ny, E = 128, 128, 5

@@ -472,3 +472,23 @@ def _assert_oracle_equals_transliteration_masked(o, cloth, what):
     assert np.array_equal(fl & (FLAG_PIN | FLAG_ACTIVE | FLAG_HIGHLIGHT), bits), f"{what}: pin/active/highlight bits"
     alive = int(np.count_nonzero(fl & FLAG_ALIVE_H) + np.count_nonzero(fl & FLAG_ALIVE_V))
     assert alive == cloth.constraints_len, f"{what}: alive sticks vs len(cloth.constraints)"
+
+
+def test_segment_quads_equal_go_transliteration(oracle):
+    """addSegment / normal (physics/cloth.go:150-168): the oracle's float32 quad corners against the transliteration, on
+    random sticks, axis-aligned ones, a zero-length one (normal = 0) and one just above the 1e-5 cut."""
+    import go_transliteration as gt
+    rng = np.random.default_rng(5)
+    segs = rng.uniform(0, 1300, (400, 4)).astype(np.float32)
+    segs[0] = (10, 20, 10, 20)                 # zero length: f32.Point{}
+    segs[1] = (10, 20, 16, 20)                 # horizontal rest-length stick
+    segs[2] = (10, 20, 10, 26)                 # vertical
+    segs[3] = (100, 100, np.float32(100.00002), 100)   # |d| ~ 2e-5: just above the cut
+    segs[4] = (100, 100, np.float32(100.000008), 100)  # ~ 8e-6: below it
+    w = gt.f32(0.6)
+    got = oracle.segment_quads(segs, 0.6)
+    for i, sg in enumerate(segs):
+        want = gt.add_segment((float(sg[0]), float(sg[1])), (float(sg[2]), float(sg[3])), w)
+        assert np.array_equal(got[i].view(np.uint32), np.array(want, np.float32).view(np.uint32)), (i, sg, got[i], want)
+    assert np.array_equal(got[0], np.array([10, 20, 10, 20, 10, 20, 10, 20], np.float32))
+    assert np.allclose(got[1], [10, 19.4, 16, 19.4, 16, 20.6, 10, 20.6])
