@@ -44,10 +44,24 @@ struct Stream1Plan {
 };
 
 // Asynchronous global -> shared copy of one lane's 16 (8 in F32) bytes; pred == false zero-fills instead of reading.
+#ifndef S1_STCS
+#define S1_STCS 0
+#endif
+#ifndef S1_LDHINT
+#define S1_LDHINT 0
+#endif
 template <int BYTES>
 __device__ __forceinline__ void cp_async_lane(void* smem, const void* gmem, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     const int n = pred ? BYTES : 0;
+#if S1_LDHINT
+    if (BYTES == 16) {
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(s), "l"(gmem), "r"(n), "l"(pol) : "memory");
+        return;
+    }
+#endif
     if (BYTES == 16)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
     else
@@ -116,9 +130,15 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         V2 ox2, oy2;
         ox2.x = pe.x, ox2.y = po.x, oy2.x = pe.y, oy2.y = po.y;
         const unsigned short ff = (unsigned short)((fe & 0xffu) | ((fo & 0xffu) << 8));
+#if S1_STCS  // streaming stores: the planes are far larger than L2 and are read again only by the NEXT frame
+        __stcs(reinterpret_cast<V2*>(out.x + at), ox2);
+        __stcs(reinterpret_cast<V2*>(out.y + at), oy2);
+        __stcs(reinterpret_cast<unsigned short*>(out.fl + at), (unsigned short)ff);
+#else
         *reinterpret_cast<V2*>(out.x + at) = ox2;
         *reinterpret_cast<V2*>(out.y + at) = oy2;
         *reinterpret_cast<unsigned short*>(out.fl + at) = ff;
+#endif
         if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {  // the neighbouring strip's ghost copy of this row
             const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + ce;
             *reinterpret_cast<V2*>(peer_up.x + pat) = ox2;
@@ -135,8 +155,13 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     auto store_prev = [&](int gy, const V2& vpx, const V2& vpy) {
         if (!own_cols || gy < ra || gy >= rb) return;
         const long long at = cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce;
+#if S1_STCS
+        __stcs(reinterpret_cast<V2*>(out.px + at), vpx);
+        __stcs(reinterpret_cast<V2*>(out.py + at), vpy);
+#else
         *reinterpret_cast<V2*>(out.px + at) = vpx;
         *reinterpret_cast<V2*>(out.py + at) = vpy;
+#endif
         if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {
             const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + ce;
             *reinterpret_cast<V2*>(peer_up.px + pat) = vpx;
