@@ -331,10 +331,20 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
         R = 128;
         const double waves = (double)(per_chunk * ((g.own_rows + R - 1) / R)) / (double)slots;
         if (waves < 6.0) {
-            const long long w = std::max<long long>(1, (long long)(waves + 0.5));
-            const long long chunks = std::max<long long>(1, w * slots / per_chunk);
-            R = (int)((g.own_rows + chunks - 1) / chunks);
-            R = std::max(8, (R + 1) & ~1);
+            auto rows_for = [&](long long w) {
+                const long long chunks = std::max<long long>(1, w * slots / per_chunk);
+                const int r = (int)((g.own_rows + chunks - 1) / chunks);
+                return std::max(8, (r + 1) & ~1);
+            };
+            long long w = std::max<long long>(1, (long long)(waves + 0.5));
+            // A launch of ONE wave starts and ends with every warp in the same phase (measured: 16384 x 2048 runs 4.6 %
+            // faster in three waves of 64-row chunks than in one wave of 206-row chunks); shorter chunks pay 4 halo rows
+            // each, so several waves are only worth it while the chunks stay long enough.
+            if (w == 1) {
+                if (rows_for(3) >= 64) w = 3;
+                else if (rows_for(2) >= 96) w = 2;
+            }
+            R = rows_for(w);
         }
     }
     pl.chunk_rows = R;
