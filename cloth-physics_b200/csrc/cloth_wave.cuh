@@ -60,6 +60,39 @@ __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 #endif
 constexpr int kWaveDepth = 3;                   // row pairs in flight in the staging ring
+#ifndef WAVE_TMA
+#define WAVE_TMA 0
+#endif
+// Optional staging by the TMA engine (-DWAVE_TMA=1; 2 = refill right after the staging reads): one elected entry thread
+// issues a bulk copy per plane row (256 columns = 2 KB in f64) that completes on a shared-memory mbarrier, instead of 128
+// threads x 8 cp.async of 16 bytes each.  Parity-green, but MEASURED 2.7 % slower than the cp.async ring on 16384^2
+// (17.5 vs 17.0 ms, profiles/README.md), so the cp.async ring stays the default.
+constexpr bool kWaveTma = WAVE_TMA != 0;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAVE_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAVE_MBAR_DONE;\n\t"
+        "bra WAVE_MBAR_WAIT;\n"
+        "WAVE_MBAR_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map: a contiguous run of bytes), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+
 #ifndef WAVE_BOTH
 #define WAVE_BOTH 0
 #endif
@@ -78,7 +111,8 @@ __host__ __device__ constexpr size_t wave_smem_bytes(int RB) {
     return (size_t)RB * kWaveHW * 2 * 2 * sizeof(T)                      // xyE, xyO
            + (size_t)RB * kWaveTW                                        // fl8
            + (size_t)(RB / 2) * kWaveHW * 2 * sizeof(uint16_t)           // stA, stB
-           + (size_t)kWaveDepth * 2 * 4 * kWaveHW * 2 * sizeof(T);       // staging: pairs x rows x planes x 128 column pairs
+           + (size_t)kWaveDepth * 2 * 4 * kWaveHW * 2 * sizeof(T)        // staging: pairs x rows x planes x 128 column pairs
+           + 64;                                                         // one mbarrier per staging slot
 }
 
 template <typename T, bool PER_CLOTH, bool DRAG>
@@ -96,9 +130,16 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     uint16_t* stA = reinterpret_cast<uint16_t*>(fl8 + (size_t)RB * TW);
     uint16_t* stB = stA + HP * HW;
     V2* stage = reinterpret_cast<V2*>(stB + HP * HW);  // [kWaveDepth][2][4][HW]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(stage + kWaveDepth * 2 * 4 * HW);  // [kWaveDepth]
 
     const int tid = threadIdx.x;
     unsigned int acc_live = 0, acc_torn = 0, acc_torn_post = 0, acc_extra = 0;
+    unsigned int stage_parity = 0;  // entry warps: bit d = phase parity of staging slot d's mbarrier (runs on across chunks)
+    if (kWaveTma && tid == kWaveWorkers) {
+        for (int d = 0; d < kWaveDepth; ++d) mbar_init(&mbar[d], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (kWaveTma) __syncthreads();
 
     // ---- the CTA's share of the work: a contiguous span of the row units of all band columns (band b of cloth e),
     // ---- laid end to end, so that every CTA streams the same number of rows whatever the cloth's shape.  A span that
@@ -178,7 +219,26 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         auto st_slot = [&](int q, int row, int plane) -> V2* {
             return stage + ((((q % kWaveDepth) * 2 + row) * 4 + plane) * HW + et);
         };
+        // columns a bulk copy brings in per plane row: this band's columns, rounded up to 16 bytes (the row padding up to
+        // `pitch` exists and is never a live particle)
+        const unsigned copy_bytes = (unsigned)((cols * (int)sizeof(T) + 15) & ~15);
         auto issue_pair = [&](int q) {  // local rows 2q, 2q+1 -> staging
+            if (kWaveTma) {
+                if (et != 0 || q > last_pair) return;  // one thread drives the TMA engine; nothing past the chunk's end
+                unsigned long long* b = &mbar[q % kWaveDepth];
+                const int rows_ok = (2 * q < n_lr ? 1 : 0) + (2 * q + 1 < n_lr ? 1 : 0);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier reads of the slot precede the refill
+                mbar_arrive_expect_tx(b, 4u * copy_bytes * (unsigned)rows_ok);
+                for (int row = 0; row < rows_ok; ++row) {
+                    const long long at = row_off(2 * q + row);
+                    V2* dst = stage + (((q % kWaveDepth) * 2 + row) * 4) * HW;
+                    bulk_g2s(dst, in.x + at, copy_bytes, b);
+                    bulk_g2s(dst + HW, in.y + at, copy_bytes, b);
+                    bulk_g2s(dst + 2 * HW, in.px + at, copy_bytes, b);
+                    bulk_g2s(dst + 3 * HW, in.py + at, copy_bytes, b);
+                }
+                return;
+            }
 #pragma unroll
             for (int row = 0; row < 2; ++row) {
                 const int lr = 2 * q + row;
@@ -212,7 +272,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             // the slots refilled in this step held the pair that set Y wrote back in step s - 2
             if (kWaveSets == 2 && s >= 2) bar_sync(kBarYDone + ((s - 2) & 3), kWaveSetThreads + kWaveEntry);
             if (q <= last_pair) {
-                cp_async_wait<kWaveDepth - 1>();
+                if (kWaveTma) {
+                    mbar_wait(&mbar[q % kWaveDepth], (stage_parity >> (q % kWaveDepth)) & 1u);
+                    stage_parity ^= 1u << (q % kWaveDepth);
+                } else {
+                    cp_async_wait<kWaveDepth - 1>();
+                }
                 const uint32_t fcur[2] = {fnext[0], fnext[1]};
                 fnext[0] = load_flags(q + 1, 0), fnext[1] = load_flags(q + 1, 1);
                 V2 p0[2], p1[2];
@@ -220,8 +285,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
 #pragma unroll
                 for (int row = 0; row < 2; ++row) {
                     const int lr = 2 * q + row;
-                    const V2 vx = *st_slot(q, row, 0), vy = *st_slot(q, row, 1);
-                    const V2 vpx = *st_slot(q, row, 2), vpy = *st_slot(q, row, 3);
+                    V2 vx = *st_slot(q, row, 0), vy = *st_slot(q, row, 1);
+                    V2 vpx = *st_slot(q, row, 2), vpy = *st_slot(q, row, 3);
+                    if (kWaveTma && !(lr < n_lr && c < cols)) {  // a bulk copy does not zero-fill what does not exist
+                        vx.x = vx.y = vy.x = vy.y = T(0);
+                        vpx = vx, vpy = vx;
+                    }
                     p0[row].x = vx.x, p1[row].x = vx.y, p0[row].y = vy.x, p1[row].y = vy.y;
                     f0[row] = fcur[row] & 0xffu, f1[row] = fcur[row] >> 8;
                     if (lr < n_lr && c < cols) {
@@ -248,7 +317,11 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                         }
                     }
                 }
-                issue_pair(q + kWaveDepth);  // refill the staging slots just read (always commits: uniform group counting)
+                if (!kWaveTma) issue_pair(q + kWaveDepth);  // refill the staging slots just read (always commits: uniform group counting)
+#if WAVE_TMA == 2  // refill as early as possible: one more entry-only barrier right after the staging reads
+                bar_sync(kBarEntry, kWaveEntry);
+                issue_pair(q + kWaveDepth);
+#endif
                 {  // H-even of sweep 0: the two rows of this column pair
                     V2* hh[2] = {&p0[0], &p0[1]};
                     V2* tt[2] = {&p1[0], &p1[1]};
@@ -279,6 +352,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 // ---- block states of this pair, derived HERE and not by sweep stage 0: the entry warps have the flags in
                 // ---- registers and time to spare, and every worker group then does the same amount of work per step ----
                 bar_sync(kBarEntry, kWaveEntry);  // the entry warps' flag bytes are in the ring
+                if (WAVE_TMA == 1) issue_pair(q + kWaveDepth);  // every entry thread has read the staging slot: refill it
                 {   // group A, pair q: rows (2q, 2q+1) x columns (2et+1, 2et+2); heads a (H, V), c (H), b (V)
                     const int er = (et + 1) & (HW - 1), cl = c + 1, cr = 2 * er;
                     const uint32_t fb = fl8[eslot * TW + cr], fd = fl8[(eslot + 1) * TW + cr];
@@ -305,7 +379,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             }
             eslot = eslot + 2 == RB ? 0 : eslot + 2;
         }
-        cp_async_wait<0>();  // nothing may still be landing in the staging slots when the next chunk starts
+        if (!kWaveTma) cp_async_wait<0>();  // nothing may still be landing in the staging slots when the next chunk starts
     } else {
         // =============================== worker warps ==============================================================
         // A thread works for the same (at most two) sweep stages and the same column pair during the whole launch, so
