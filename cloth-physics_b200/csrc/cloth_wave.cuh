@@ -48,8 +48,11 @@ constexpr int kWaveGroups = kWaveWorkers / 64;  // worker groups of 64 column pa
 // one set's barrier waits, loads and address arithmetic overlap the other set's binary64 work on the same scheduler.
 constexpr int kWaveSets = WAVE_SETS;
 constexpr bool kWaveStagger = WAVE_STAGGER != 0;  // Y may start step s only after X's alpha phase of step s
-constexpr int kBarEntry = 1, kBarX = 2, kBarY = 3, kBarXDone = 4 /* .. 7 */, kBarYDone = 8 /* .. 11 */;
+constexpr int kBarEntry = 1, kBarX = 2, kBarY = 3, kBarXDone = 4 /* .. 7 */, kBarYDone = 8 /* .. 11 */, kBarXEnd = 12;
 constexpr int kWaveSetThreads = kWaveWorkers / 2;
+// With two worker sets the entry warps also write the finished rows back to HBM (they wait for "set Y has finished step
+// s - 2" before they refill those ring slots anyway), so the last sweep stage does the same work as every other stage.
+constexpr bool kWaveEntryStores = kWaveSets == 2;
 static_assert(kWaveSets == 1 || kWaveWorkers == 512, "the two-set stage mapping is written for 8 worker groups");
 
 #ifdef WAVE_ABLATE_BAR  // timing experiment only (results are wrong): what do the barriers cost?
@@ -271,6 +274,39 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             const int q = s + 1;  // the pair delivered during this step
             // the slots refilled in this step held the pair that set Y wrote back in step s - 2
             if (kWaveSets == 2 && s >= 2) bar_sync(kBarYDone + ((s - 2) & 3), kWaveSetThreads + kWaveEntry);
+            if (kWaveEntryStores) {
+                // ---- the pair that has passed all K sweeps (local rows 2qo, 2qo+1, in the ring slots refilled below) leaves ----
+                const int qo = q - HP;
+                if (qo >= 1 && c >= lx0 && c < lx1) {
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int lr = 2 * qo + w;
+                        if (lr >= ly0 && lr < ly1) {
+                            const V2 pe = xyE[(eslot + w) * HW + et], po = xyO[(eslot + w) * HW + et];
+                            const uint32_t ff = *reinterpret_cast<const uint16_t*>(fl8 + (eslot + w) * TW + c);
+                            const long long at = row_off(lr) + c;
+                            const int gy = y0 + lr - 2, gx = ox + c;
+                            V2 ox2, oy2;
+                            ox2.x = pe.x, ox2.y = po.x, oy2.x = pe.y, oy2.y = po.y;
+                            *reinterpret_cast<V2*>(out.x + at) = ox2;
+                            *reinterpret_cast<V2*>(out.y + at) = oy2;
+                            *reinterpret_cast<unsigned short*>(out.fl + at) = (unsigned short)ff;
+                            if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {
+                                const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + gx;
+                                *reinterpret_cast<V2*>(peer_up.x + pat) = ox2;
+                                *reinterpret_cast<V2*>(peer_up.y + pat) = oy2;
+                                *reinterpret_cast<unsigned short*>(peer_up.fl + pat) = (unsigned short)ff;
+                            }
+                            if (gy >= peer_dn.row_lo && gy < peer_dn.row_hi) {
+                                const long long pat = (long long)e * peer_dn.cloth_stride + (long long)(gy - peer_dn.held_row0) * g.pitch + gx;
+                                *reinterpret_cast<V2*>(peer_dn.x + pat) = ox2;
+                                *reinterpret_cast<V2*>(peer_dn.y + pat) = oy2;
+                                *reinterpret_cast<unsigned short*>(peer_dn.fl + pat) = (unsigned short)ff;
+                            }
+                        }
+                    }
+                }
+            }
             if (q <= last_pair) {
                 if (kWaveTma) {
                     mbar_wait(&mbar[q % kWaveDepth], (stage_parity >> (q % kWaveDepth)) & 1u);
@@ -371,8 +407,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 fprev[0] = f0[1], fprev[1] = f1[1];
             }
             if (kWaveSets == 2) {
-                bar_sync(kBarX, kWaveSetThreads + kWaveEntry);  // end of set X's phase alpha
-                bar_sync(kBarX, kWaveSetThreads + kWaveEntry);  // end of set X's phase beta
+                // The pair delivered in step s is first read in step s + 1, and nothing it writes is touched by set X
+                // before: the entry warps only join the END-of-step barrier, so they have the whole step for their work
+                // (one entry warp per scheduler gets a fifth of the issue slots: ~760 instructions take about a phase).
+                bar_sync(kBarXEnd, kWaveSetThreads + kWaveEntry);
             } else {
                 __syncthreads();  // end of phase alpha
                 __syncthreads();  // end of phase beta
@@ -530,7 +568,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             }
 #pragma unroll
             for (int n = 0; n < NI; ++n) {
-                if (jn[n] + 1 < K) {
+                if (kWaveEntryStores || jn[n] + 1 < K) {
                     xyE[sa[n] * HW + k] = pa[n], xyO[sa[n] * HW + k] = pc[n], xyE[sb[n] * HW + k] = pb[n], xyO[sb[n] * HW + k] = pd[n];
                 } else if (ce >= lx0 && ce < lx1) {
                     // ---- the last colour pass is done: rows 2p+1 and 2p+2 leave through the registers --------------------------
@@ -588,7 +626,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 }
             }
             if (kWaveSets == 2) {
-                bar_sync(set ? kBarY : kBarX, set ? kWaveSetThreads : kWaveSetThreads + kWaveEntry);
+                bar_sync(set ? kBarY : kBarX, kWaveSetThreads);  // (the set's workers only)
                 if (kWaveStagger && set == 0 && s >= 1) bar_arrive(kBarXDone + ((s - 1) & 3), kWaveWorkers);
             } else {
                 __syncthreads();
@@ -611,7 +649,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 }
             }
             if (kWaveSets == 2) {
-                bar_sync(set ? kBarY : kBarX, set ? kWaveSetThreads : kWaveSetThreads + kWaveEntry);
+                if (set) bar_sync(kBarY, kWaveSetThreads);
+                else bar_sync(kBarXEnd, kWaveSetThreads + kWaveEntry);  // with the entry warps: the next pair is in the ring
                 if (set == 0) {
                     if (!kWaveStagger && s + 1 < n_steps) bar_arrive(kBarXDone + (s & 3), kWaveWorkers);  // X has finished step s
                 } else if (s + 2 < n_steps) {
