@@ -626,7 +626,9 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 }
             }
             if (kWaveSets == 2) {
-                bar_sync(set ? kBarY : kBarX, kWaveSetThreads);  // (the set's workers only)
+                // B_j only needs A_j of the same stage: the alpha barrier spans the two half-band groups that share
+                // their stages (4 warps, one per scheduler), not the whole set
+                bar_sync(set ? 14 + ((grp >> 1) & 1) : ((grp & 2) ? 13 : kBarX), kWaveSetThreads / 2);  // ids 2, 13 (X), 14, 15 (Y)
                 if (kWaveStagger && set == 0 && s >= 1) bar_arrive(kBarXDone + ((s - 1) & 3), kWaveWorkers);
             } else {
                 __syncthreads();
