@@ -6,22 +6,26 @@
 // Here a CTA owns a band of 256 columns and a chunk of rows, and streams the rows downwards:
 //
 //     entry    rows (2q, 2q+1) arrive (cp.async staging ring, three pairs ahead), particle loop (cloth.go:92-94),
-//              H-even of sweep 0, then they join the ring of 4K+4 rows
+//              H-even of sweep 0, the state words of their 2x2 blocks, then they join the ring of 4K+4 rows; the pair
+//              that has passed all K sweeps leaves for HBM from the ring slots the new pair is about to take
 //     stage j  (sweep j, j = 0..K-1) works 2 row pairs behind stage j-1:
 //                A_j(p) = H-odd(j) + V-even(j)    on rows (2p,   2p+1),   at step s = p + 2j
 //                B_j(p) = V-odd(j) + H-even(j+1)  on rows (2p+1, 2p+2),   at step s = p + 2j + 1
-//              (the same 2x2-blocks-in-registers passes as the tile kernel); B_{K-1} writes its rows back to HBM
+//              (the same 2x2-blocks-in-registers passes as the tile kernel)
 //
-// A step = { all A_j, entry of the next pair } barrier { all B_j } barrier, so every barrier interval carries the work
-// of all K sweeps.  Dependencies: B_j(p) needs A_j(p) (previous step) and A_j(p+1) (same step, before the barrier);
+// A step = { all A_j } barrier { all B_j } barrier with the entry work alongside, so every barrier interval carries the
+// work of all K sweeps.  Dependencies: B_j(p) needs A_j(p) (previous step) and A_j(p+1) (same step, before the barrier);
 // A_{j+1}(p) needs B_j(p-1) and B_j(p) (both in earlier steps) — hence the lag of two pairs per sweep.
 // Rows are never recomputed (only the 2K halo rows above and below a chunk, trapezoid-wise as in the tile kernel), the
 // column halo is 2K of 256 instead of 2K of 128, and HBM traffic is spread evenly over the whole launch.
 //
-// Threads: 16 worker warps (8 groups of 64 column pairs; a phase has 2K half-band items, group g takes items g, g+8)
-// + 4 entry warps (one column pair per thread).  Validity of the stale rim is decided per item (rows, warp-uniform) and per thread and stage
-// (columns), exactly as in the tile kernel.  Local rows are offset by 2 so that pair 0 is an all-zero dummy pair:
-// B_j(0) = rows (1, 2) then gives the first real row its H-even pass without a special case.
+// Threads: 16 worker warps (8 groups of 64 column pairs; a group serves two stages of one half-band) in two sets
+// (stages 0..K/2-1 and the rest, see kWaveSets below) + 4 entry warps (one column pair per thread).  Every worker group
+// executes the same instruction count per step; everything that is not a sweep is the entry warps' job, and they only
+// join the end-of-step barrier (they have a whole step for their ~800 instructions at a fifth of a scheduler's issue
+// slots).  Validity of the stale rim is decided per item (rows, warp-uniform) and per thread and stage (columns),
+// exactly as in the tile kernel.  Local rows are offset by 2 so that pair 0 is an all-zero dummy pair: B_j(0) = rows
+// (1, 2) then gives the first real row its H-even pass without a special case.
 #pragma once
 #include <type_traits>
 
@@ -42,10 +46,13 @@ constexpr int kWaveGroups = kWaveWorkers / 64;  // worker groups of 64 column pa
 #ifndef WAVE_STAGGER
 #define WAVE_STAGGER 0
 #endif
-// Two worker sets: set X (groups 0-3, with the entry warps) runs the first half of the sweep stages, set Y (groups 4-7) the
-// second half.  Each set has its own pair of barriers per step; the sets are chained by two producer/consumer barriers
-// ("X has finished step s", "Y has finished step s": bar.arrive / bar.sync), so they may drift apart by up to one step and
-// one set's barrier waits, loads and address arithmetic overlap the other set's binary64 work on the same scheduler.
+// Two worker sets: set X (groups 0-3) runs the first half of the sweep stages, set Y (groups 4-7) the second half.
+// Barriers per step: alpha -> beta among the two groups that share their stages (128 threads: B_j only needs A_j),
+// end of step within a set (X's with the entry warps); the sets are chained by two producer/consumer barriers ("X has
+// finished step s", "Y has finished step s": bar.arrive / bar.sync), so they may drift apart by up to one step and one
+// set's barrier waits, loads and address arithmetic overlap the other set's binary64 work on the same scheduler.
+// Named barriers: 1 entry warps only; 2, 13 (X) and 14, 15 (Y) alpha -> beta; 12 end of step X + entry; 3 end of step Y;
+// 4-7 "X done" and 8-11 "Y done" (step mod 4).
 constexpr int kWaveSets = WAVE_SETS;
 constexpr bool kWaveStagger = WAVE_STAGGER != 0;  // Y may start step s only after X's alpha phase of step s
 constexpr int kBarEntry = 1, kBarX = 2, kBarY = 3, kBarXDone = 4 /* .. 7 */, kBarYDone = 8 /* .. 11 */, kBarXEnd = 12;
