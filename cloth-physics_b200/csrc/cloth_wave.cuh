@@ -70,6 +70,12 @@ __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 #endif
 constexpr int kWaveDepth = 3;                   // row pairs in flight in the staging ring
+#ifndef WAVE_SLACK
+#define WAVE_SLACK 0
+#endif
+// extra row pairs in the ring beyond the 2K + 2 the pipeline needs: set X (with the entry warps) may then run that many
+// more steps ahead of set Y before the entry warps must wait for Y (2 + kWaveSlack steps)
+constexpr int kWaveSlack = WAVE_SLACK;
 #ifndef WAVE_TMA
 #define WAVE_TMA 0
 #endif
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     // (stA of pair 0 is never read: A_j(0) is skipped; stB of pair 0 is written by the entry warps at step 0)
 
     const int last_pair = (n_lr + 1) >> 1;  // entry also delivers one all-zero pair past the end (row n_lr may be a B tail)
-    const int n_steps = last_pair + 2 * K + 1;
+    const int n_steps = last_pair + 2 * K + 1 + kWaveSlack;  // (the last pair leaves the ring 2K + 2 + slack steps after it came)
 
     // ---- the state word of a 2x2 block (cloth_fused.cuh): live bits of its four sticks, pin bits of its corners ------
     auto live_bit = [](uint32_t fh, uint32_t ft, uint32_t alive) -> uint32_t {
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         for (int s = 0; s < n_steps; ++s) {
             const int q = s + 1;  // the pair delivered during this step
             // the slots refilled in this step held the pair that set Y wrote back in step s - 2
-            if (kWaveSets == 2 && s >= 2) bar_sync(kBarYDone + ((s - 2) & 3), kWaveSetThreads + kWaveEntry);
+            if (kWaveSets == 2 && s >= 2 + kWaveSlack) bar_sync(kBarYDone + ((s - 2 - kWaveSlack) & 3), kWaveSetThreads + kWaveEntry);
             if (kWaveEntryStores) {
                 // ---- the pair that has passed all K sweeps (local rows 2qo, 2qo+1, in the ring slots refilled below) leaves ----
                 const int qo = q - HP;
@@ -662,7 +668,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 else bar_sync(kBarXEnd, kWaveSetThreads + kWaveEntry);  // with the entry warps: the next pair is in the ring
                 if (set == 0) {
                     if (!kWaveStagger && s + 1 < n_steps) bar_arrive(kBarXDone + (s & 3), kWaveWorkers);  // X has finished step s
-                } else if (s + 2 < n_steps) {
+                } else if (s + 2 + kWaveSlack < n_steps) {
                     bar_arrive(kBarYDone + (s & 3), kWaveSetThreads + kWaveEntry);  // Y has finished step s: its slots may be refilled
                 }
             } else {

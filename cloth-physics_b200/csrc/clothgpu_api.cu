@@ -391,7 +391,7 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     WavePlan pl{};
     pl.K = u.iterations;
     pl.h = 2 * pl.K;
-    pl.RB = 4 * pl.K + 4;
+    pl.RB = 4 * pl.K + 4 + 2 * kWaveSlack;
     if (g.nx <= kWaveTW) {
         pl.bands = 1;
         pl.first_w = kWaveTW;
