@@ -518,12 +518,13 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     int sched = c->schedule;
     if (sched == CLOTHGPU_SCHED_AUTO) {
         // One sweep: the row-streaming kernel, unless the cloth is too small to feed enough independent warps.
-        // 6..8 sweeps on cloths that fill the 256-column bands and amortise the pipeline ramp: the wavefront kernel
-        // (measured on 4096^2: slower than the tile kernel up to 4 sweeps, level at 6, 1.19x faster at 8).
+        // 4..8 sweeps on cloths that fill the 256-column bands and amortise the pipeline ramp: the wavefront kernel
+        // (measured on 4096^2 against the tile kernel: 0.617 vs 0.569 ms at 3 sweeps, 0.683 vs 0.704 at 4, 0.734 vs
+        // 0.854 at 5, 0.97 vs 1.48 at 8).
         const long long warps = (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble;
         if (u0.iterations == 1 && c->k1_stream && warps >= 2ll * c->sm_count)
             sched = CLOTHGPU_SCHED_ROWSTREAM;
-        else if (u0.iterations >= 6 && u0.iterations <= kMaxSweepsPerLaunch && c->wave_auto && c->g.nx >= 192 && c->g.own_rows >= 256)
+        else if (u0.iterations >= 4 && u0.iterations <= kMaxSweepsPerLaunch && c->wave_auto && c->g.nx >= 192 && c->g.own_rows >= 256)
             sched = CLOTHGPU_SCHED_WAVE;
         else
             sched = CLOTHGPU_SCHED_FUSED;
