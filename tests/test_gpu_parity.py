@@ -172,6 +172,69 @@ def test_live_stick_list_matches_reference_render_order(oracle):
     assert np.all(idx[:, 1] > idx[:, 0])
 
 
+def _expected_segments_fast(nx, ny, x, y, fl):
+    """_expected_segments with numpy (creation order: by tail particle, the vertical stick before the horizontal one)."""
+    x32, y32 = x.astype(np.float32).reshape(ny, nx), y.astype(np.float32).reshape(ny, nx)
+    f2 = fl.reshape(ny, nx)
+    act, hi = (f2 & FLAG_ACTIVE) != 0, (f2 & FLAG_HIGHLIGHT) != 0
+    v = np.zeros((ny, nx), bool)
+    h = np.zeros((ny, nx), bool)
+    v[1:] = ((f2[:-1] & FLAG_ALIVE_V) != 0) & act[:-1] & act[1:]          # stick from the particle above
+    h[:, 1:] = ((f2[:, :-1] & FLAG_ALIVE_H) != 0) & act[:, :-1] & act[:, 1:]  # ... from the particle to the left
+    segs, hl = [], []
+    order = np.zeros((ny, nx, 2), bool)
+    order[..., 0], order[..., 1] = v, h
+    rr, cc, kind = np.nonzero(order)      # row-major over (row, column, [vertical, horizontal]) = creation order
+    hr, hc = rr - (kind == 0), cc - (kind == 1)
+    segs = np.stack([x32[hr, hc], y32[hr, hc], x32[rr, cc], y32[rr, cc]], axis=1)
+    hl = (hi[hr, hc] & hi[rr, cc]).astype(np.uint8)
+    return segs.astype(np.float32).reshape(-1, 4), hl
+
+
+@pytest.mark.parametrize("nx,ny,ens", [(171, 36, 1), (700, 90, 2), (1037, 1100, 1), (16, 300, 3), (2, 9, 1), (4100, 64, 1)])
+def test_live_stick_list_on_random_states(nx, ny, ens):
+    """The compaction kernels on shapes whose rows are shorter / longer than a warp's 512 particles, odd widths (row
+    padding), several scatter blocks, an ensemble member other than 0: random dead sticks, holes and highlights."""
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, ensemble=ens)
+    g = clothgpu.Cloth(desc)
+    rng = np.random.default_rng(nx + ny)
+    for e in range(ens):
+        x, y, px, py, fl = random_state(nx, ny, seed=nx * 3 + e, kill=0.1, holes=0.05)
+        fl[rng.random(fl.size) < 0.3] |= FLAG_HIGHLIGHT
+        g.write_state(x, y, px, py, fl, cloth=e)
+    e = ens - 1
+    x, y, px, py, fl = g.read_state(cloth=e)
+    want, want_hl = _expected_segments_fast(nx, ny, x, y, fl)
+    got, got_hl, idx = g.read_segments(cloth=e, with_indices=True)
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got_hl, want_hl)
+    if len(idx):
+        d = idx[:, 1].astype(np.int64) - idx[:, 0]
+        assert np.all((d == 1) | (d == nx)) and np.all(np.diff(idx[:, 1].astype(np.int64)) >= 0)
+    if nx <= 200:  # the slow reference loop agrees with the vectorised one
+        w2, h2 = _expected_segments(nx, ny, x, y, fl)
+        assert np.array_equal(w2, want) and np.array_equal(h2, want_hl)
+
+
+def test_live_stick_lists_of_two_strips_concatenate_to_the_whole_cloth():
+    """A strip lists the sticks whose TAIL it owns; the vertical sticks of its first row hang from the ghost row above."""
+    nx, ny, split = 333, 80, 34
+    whole = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=1)
+    up = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=1, strip_row0=0, strip_rows=split)
+    lo = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=1, strip_row0=split, strip_rows=ny - split)
+    g, gu, gl = clothgpu.Cloth(whole), clothgpu.Cloth(up), clothgpu.Cloth(lo)
+    st = random_state(nx, ny, seed=9, kill=0.1, holes=0.05)
+    g.write_state(*st)
+    gu.write_state(*[a.reshape(ny, nx)[:split].ravel() for a in st])
+    gl.write_state(*[a.reshape(ny, nx)[split:].ravel() for a in st])
+    _exchange_halos_same_device(gu, gl)
+    sw, hw = g.read_segments()
+    su, hu = gu.read_segments()
+    sl, hl = gl.read_segments()
+    assert len(su) + len(sl) == len(sw)
+    assert np.array_equal(np.concatenate([su, sl]), sw) and np.array_equal(np.concatenate([hu, hl]), hw)
+
+
 def test_outline_quads_match_addsegment_of_the_reference(oracle):
     """clothgpu_read_quads_f32 = addSegment / normal (physics/cloth.go:150-168) over the live-stick list: bit-exact float32
     against the oracle's restatement on the state the scripted trace leaves (torn, punched, highlighted)."""
