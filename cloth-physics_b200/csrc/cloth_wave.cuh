@@ -120,6 +120,17 @@ struct WavePlan {
     int first_w, mid_w;
     int columns;      // band columns = bands * ensemble
     int span;         // row units per CTA (even)
+    // Packed ensembles (pack != 0): cloths of at most 128 columns, two side by side in the 256-column band and many stacked
+    // on top of each other, streamed as ONE tall virtual cloth (the Geom handed to the kernel describes the virtual cloth:
+    // nx = 256, rows = pairs * rows_v).  A cloth's last column and last row head no stick, so the members do not interact;
+    // no halo at all and one pipeline fill per CTA instead of per cloth.  Only the entry warps know about it: the
+    // real geometry below tells them where a ring row lives.
+    int pack;
+    int nx, ny;       // real cloth size
+    int rows_v;       // virtual rows per cloth (ny rounded up to even: row pairs never mix two cloths)
+    int ensemble;     // real number of cloths
+    int pitch;        // real elements between rows
+    long long cloth_stride;  // real elements between cloths
 };
 
 template <typename T>
@@ -131,7 +142,7 @@ __host__ __device__ constexpr size_t wave_smem_bytes(int RB) {
            + 64;                                                         // one mbarrier per staging slot
 }
 
-template <typename T, bool PER_CLOTH, bool DRAG>
+template <typename T, bool PER_CLOTH, bool DRAG, bool PACK = false>
 __global__ void __launch_bounds__(kWaveThreads, 1)
     wave_frame_kernel(Planes<T> in, Planes<T> out, Geom g, WavePlan pl, const FrameU<T> u0,
                       const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr, const PeerOut<T> peer_up,
@@ -232,6 +243,35 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         // =============================== entry warps ===============================================================
         const int et = tid - kWaveWorkers;  // 0..127: the column pair this thread delivers, both rows of a pair
         const int c = 2 * et;
+        // where local row lr of this thread's column pair lives in HBM, and whether it exists at all
+        const int pk_half = PACK ? et >> 6 : 0, pk_cc = PACK ? 2 * (et & 63) : c;
+        const int col_end = PACK ? pl.nx : cols;  // the pair's first column exists iff pk_cc < col_end
+        int pk_lr = 2, pk_m = 0, pk_rr = 0;  // packed ensembles: local row 2q of the pair being delivered = row pk_rr of cloth pair pk_m
+        if (PACK) pk_m = y0 / pl.rows_v, pk_rr = y0 - pk_m * pl.rows_v;
+        struct RowAt {
+            long long at;   // element offset of (row, first column of the pair)
+            bool ok;        // the row exists (and the pair's first column with it)
+            bool last_row;  // packed ensembles: the cloth's last row heads no vertical stick
+        };
+        auto row_at = [&](int lr) -> RowAt {
+            RowAt r;
+            r.last_row = false;
+            if (!PACK) {
+                r.ok = lr >= 2 && lr < n_lr && c < cols;
+                r.at = r.ok ? row_off(lr) + c : 0;
+                return r;
+            }
+            // (cloth pair, row) of lr from those of the pair being delivered: the rows asked for are at most 2K + 2 pairs
+            // behind and kWaveDepth pairs ahead, so a few steps instead of a division
+            int rr = pk_rr + (lr - pk_lr), m = pk_m;
+            while (rr >= pl.rows_v) rr -= pl.rows_v, ++m;
+            while (rr < 0) rr += pl.rows_v, --m;
+            const int cid = 2 * m + pk_half;
+            r.ok = lr >= 2 && lr < n_lr && rr < pl.ny && cid < pl.ensemble && pk_cc < pl.nx;
+            r.at = r.ok ? (long long)cid * pl.cloth_stride + (long long)rr * pl.pitch + pk_cc : 0;
+            r.last_row = rr == pl.ny - 1;
+            return r;
+        };
         auto st_slot = [&](int q, int row, int plane) -> V2* {
             return stage + ((((q % kWaveDepth) * 2 + row) * 4 + plane) * HW + et);
         };
@@ -257,9 +297,9 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             }
 #pragma unroll
             for (int row = 0; row < 2; ++row) {
-                const int lr = 2 * q + row;
-                const bool ok = q >= 1 && lr < n_lr && c < cols;
-                const long long at = ok ? row_off(lr) + c : 0;
+                const RowAt ra_ = row_at(2 * q + row);
+                const bool ok = ra_.ok;
+                const long long at = ra_.at;
                 cp_async_lane<sizeof(V2)>(st_slot(q, row, 0), in.x + at, ok);
                 cp_async_lane<sizeof(V2)>(st_slot(q, row, 1), in.y + at, ok);
                 cp_async_lane<sizeof(V2)>(st_slot(q, row, 2), in.px + at, ok);
@@ -268,11 +308,21 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             cp_async_commit();
         };
         auto load_flags = [&](int q, int row) -> uint32_t {
-            const int lr = 2 * q + row;
+            const RowAt ra_ = row_at(2 * q + row);
             uint32_t f = 0;
-            if (q >= 1 && lr < n_lr && c < cols) {
-                f = *reinterpret_cast<const unsigned short*>(in.fl + row_off(lr) + c);
-                if (c + 1 >= cols) f &= 0xffu;  // column nx (row padding) does not exist
+            if (ra_.ok) {
+                f = *reinterpret_cast<const unsigned short*>(in.fl + ra_.at);
+                if (pk_cc + 1 >= col_end) f &= 0xffu;  // column nx (row padding) does not exist
+                if (PACK) {
+                    // Next to / below a cloth's edge lies ANOTHER cloth here: the edge particles must head no stick.  Their
+                    // alive bits (meaningless, but part of the state the caller may have written) are parked in the spare
+                    // bits 5 / 6 of the flag byte — no pass looks at those — and restored when the row is written back.
+                    uint32_t hide = 0;
+                    if (ra_.last_row) hide |= CLOTHGPU_FLAG_ALIVE_V | (CLOTHGPU_FLAG_ALIVE_V << 8);
+                    if (pk_cc == pl.nx - 1) hide |= CLOTHGPU_FLAG_ALIVE_H;
+                    if (pk_cc + 1 == pl.nx - 1) hide |= CLOTHGPU_FLAG_ALIVE_H << 8;
+                    f = (f & ~hide) | ((f & hide) << 2);  // ALIVE_H (8) -> 0x20, ALIVE_V (16) -> 0x40
+                }
             }
             return f;
         };
@@ -294,10 +344,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
 #pragma unroll
                     for (int w = 0; w < 2; ++w) {
                         const int lr = 2 * qo + w;
-                        if (lr >= ly0 && lr < ly1) {
+                        const RowAt ra_ = row_at(lr);
+                        if (lr >= ly0 && lr < ly1 && ra_.ok) {
                             const V2 pe = xyE[(eslot + w) * HW + et], po = xyO[(eslot + w) * HW + et];
-                            const uint32_t ff = *reinterpret_cast<const uint16_t*>(fl8 + (eslot + w) * TW + c);
-                            const long long at = row_off(lr) + c;
+                            uint32_t ff = *reinterpret_cast<const uint16_t*>(fl8 + (eslot + w) * TW + c);
+                            if (PACK) ff = (ff & 0x1f1fu) | ((ff & 0x6060u) >> 2);  // the parked edge bits come back
+                            const long long at = ra_.at;
                             const int gy = y0 + lr - 2, gx = ox + c;
                             V2 ox2, oy2;
                             ox2.x = pe.x, ox2.y = po.x, oy2.x = pe.y, oy2.y = po.y;
@@ -342,12 +394,13 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     }
                     p0[row].x = vx.x, p1[row].x = vx.y, p0[row].y = vy.x, p1[row].y = vy.y;
                     f0[row] = fcur[row] & 0xffu, f1[row] = fcur[row] >> 8;
-                    if (lr < n_lr && c < cols) {
+                    const RowAt ra_ = row_at(lr);
+                    if (ra_.ok) {
                         T px0 = vpx.x, px1 = vpx.y, py0 = vpy.x, py1 = vpy.y;
                         particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], u);
-                        if (c + 1 < cols) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
+                        if (pk_cc + 1 < col_end) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
                         if (owned(lr, c)) {  // the owner of a particle writes its previous position
-                            const long long at = row_off(lr) + c;
+                            const long long at = ra_.at;
                             const int gy = y0 + lr - 2, gx = ox + c;
                             V2 ox2, oy2;
                             ox2.x = px0, ox2.y = px1, oy2.x = py0, oy2.y = py1;
@@ -429,6 +482,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 __syncthreads();  // end of phase beta
             }
             eslot = eslot + 2 == RB ? 0 : eslot + 2;
+            if (PACK) {
+                pk_lr += 2, pk_rr += 2;
+                if (pk_rr >= pl.rows_v) pk_rr -= pl.rows_v, ++pk_m;
+            }
         }
         if (!kWaveTma) cp_async_wait<0>();  // nothing may still be landing in the staging slots when the next chunk starts
     } else {

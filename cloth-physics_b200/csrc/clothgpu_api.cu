@@ -86,6 +86,7 @@ struct clothgpu {
     int s1_chunk_rows = 0;   // 0: chosen per launch
     int wave_chunk_rows = 0; // 0: chosen per launch
     int wave_auto = 1;       // AUTO may pick the wavefront kernel
+    int wave_pack = 1;       // ensembles of narrow cloths run on the wavefront kernel as one tall virtual cloth
     int s1_ring = 2;         // shared-memory prefetch ring depth of stream1_frame_kernel (0: register prefetch)
     int s1_warps_per_sm = 4 * S1_RING_CTAS;  // resident warps of stream1_frame_kernel per SM (its launch bounds)
     // All state planes and the strip epoch slots live in ONE device allocation, so a neighbouring strip (another
@@ -385,10 +386,28 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
 }
 
 // 2..8 sweeps per frame: the wavefront kernel (cloth_wave.cuh).
+// Ensembles of cloths of at most 128 columns run on the wavefront kernel as ONE tall virtual cloth: two cloths side by
+// side in the 256-column band, the pairs stacked on top of each other (cloth_wave.cuh, WavePlan::pack).
+static bool wave_packable(const clothgpu* c, bool per_cloth_frames) {
+    const Geom& g = c->g;
+    return c->wave_pack && !per_cloth_frames && c->desc.strip_rows <= 0 && g.ensemble >= 2 && g.nx <= kWaveTW / 2 && g.own_rows == g.held_rows &&
+           (long long)((g.ensemble + 1) / 2) * ((g.own_rows + 1) & ~1) < (1ll << 30);
+}
+
 template <typename T>
 int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
-    const Geom& g = c->g;
+    Geom g = c->g;
     WavePlan pl{};
+    if (wave_packable(c, per_cloth != nullptr)) {
+        pl.pack = 1;
+        pl.nx = g.nx, pl.ny = g.own_rows, pl.rows_v = (g.own_rows + 1) & ~1, pl.ensemble = g.ensemble;
+        pl.pitch = g.pitch, pl.cloth_stride = g.cloth_stride;
+        // the virtual cloth the kernel streams (its pitch / cloth_stride are not used: the entry warps map rows themselves)
+        g.nx = kWaveTW;
+        g.own_rows = g.held_rows = ((pl.ensemble + 1) / 2) * pl.rows_v;
+        g.own_row0 = g.held_row0 = 0;
+        g.ensemble = 1;
+    }
     pl.K = u.iterations;
     pl.h = 2 * pl.K;
     pl.RB = 4 * pl.K + 4 + 2 * kWaveSlack;
@@ -410,7 +429,9 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     long long span = c->wave_chunk_rows;
     if (span < 2) {
         long long ctas = c->sm_count;
-        while (total / ctas > 640) ctas += c->sm_count;
+        // (packed ensembles have no row halo to amortise and a costlier entry side: one wave of long spans measured
+        //  best, 1.96 vs 2.05 ms on 2048 cloths of 128^2)
+        while (total / ctas > (pl.pack ? 4096 : 640)) ctas += c->sm_count;
         span = (total + ctas - 1) / ctas;
         span = std::max<long long>(2 * pl.h, (span + 1) & ~1ll);
     }
@@ -433,6 +454,8 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     };
     if (pc)
         CU_TRY(go(wave_frame_kernel<T, true, true>));
+    else if (pl.pack)
+        CU_TRY(drag ? go(wave_frame_kernel<T, false, true, true>) : go(wave_frame_kernel<T, false, false, true>));
     else if (drag)
         CU_TRY(go(wave_frame_kernel<T, false, true>));
     else
@@ -524,7 +547,9 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         const long long warps = (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble;
         if (u0.iterations == 1 && c->k1_stream && warps >= 2ll * c->sm_count)
             sched = CLOTHGPU_SCHED_ROWSTREAM;
-        else if (u0.iterations >= 4 && u0.iterations <= kMaxSweepsPerLaunch && c->wave_auto && c->g.nx >= 192 && c->g.own_rows >= 256)
+        else if (u0.iterations >= 4 && u0.iterations <= kMaxSweepsPerLaunch && c->wave_auto &&
+                 ((c->g.nx >= 192 && c->g.own_rows >= 256) ||
+                  (wave_packable(c, dev_frames != nullptr) && (long long)c->g.ensemble * c->g.own_rows >= 256ll * c->sm_count)))
             sched = CLOTHGPU_SCHED_WAVE;
         else
             sched = CLOTHGPU_SCHED_FUSED;
@@ -713,6 +738,7 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     if (const char* s = getenv("CLOTHGPU_S1_ROWS")) c->s1_chunk_rows = atoi(s) & ~1;
     if (const char* s = getenv("CLOTHGPU_WAVE_ROWS")) c->wave_chunk_rows = atoi(s) & ~1;
     if (const char* s = getenv("CLOTHGPU_WAVE_AUTO")) c->wave_auto = atoi(s);
+    if (const char* s = getenv("CLOTHGPU_WAVE_PACK")) c->wave_pack = atoi(s);
     if (const char* s = getenv("CLOTHGPU_S1_RING")) {
         c->s1_ring = atoi(s);
         c->s1_warps_per_sm = c->s1_ring == 2 ? 4 * S1_RING_CTAS : 4 * S1_MIN_CTAS;  // (3 stages: 48 KB per CTA, 4 CTAs fit)

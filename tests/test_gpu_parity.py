@@ -293,6 +293,37 @@ def test_ensemble_cloths_are_independent(oracle, K, schedule):
         assert_same_state(g.read_state(cloth=e), oracles[e].read_state(), f"cloth {e} shared frame")
 
 
+@pytest.mark.parametrize("nx,ny,E,K", [(128, 128, 6, 8), (100, 91, 7, 8), (64, 40, 9, 4), (17, 300, 3, 5), (128, 130, 2, 6)])
+def test_packed_ensembles_on_the_wavefront_kernel(oracle, nx, ny, E, K):
+    """Ensembles of narrow cloths run on the wavefront kernel as one tall virtual cloth: two cloths side by side in the
+    256-column band, the pairs stacked (WavePlan::pack).  Odd member counts (an empty right half), odd heights (a padding
+    row per cloth), widths that are not a multiple of 16, tears and holes: every member must equal the oracle run on that
+    cloth alone, bit for bit, and the flag bytes of the cloth edges must survive the trip."""
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, ensemble=E, max_iterations=K)
+    g = clothgpu.Cloth(desc)
+    g.set_schedule(SCHED_WAVE)
+    one = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=K)
+    oracles = [oracle.OracleCloth(one, oracle.COLOUR) for _ in range(E)]
+    for e in range(E):
+        st = random_state(nx, ny, seed=1000 + 17 * e + nx)
+        g.write_state(*st, cloth=e)
+        oracles[e].write_state(*st)
+    f = _abi.default_frame(K)
+    f.win_w, f.win_h = 128 + 6 * nx + 50, 164 + 6 * ny + 20
+    f.buttons = MOUSE_DRAGGING
+    f.tear_length = 9.5
+    f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py = 128.0 + 3 * nx, 164.0 + 3 * ny, 120.0 + 3 * nx, 170.0 + 3 * ny
+    relax = 0
+    for t in range(3):
+        g.step(f)
+        for e in range(E):
+            oracles[e].step(f)
+    for e in range(E):
+        assert_same_state(g.read_state(cloth=e), oracles[e].read_state(), f"{nx}x{ny} K={K} cloth {e} of {E}")
+        relax += oracles[e].relaxations
+    assert g.counters()["relaxations"] == relax
+
+
 def _cudart():
     import glob
     import os
