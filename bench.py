@@ -367,7 +367,7 @@ def main():
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     suffix = "<double>" if args.precision == "f64" else "<float>"
     kernel = ("stream1_frame_kernel" if (K == 1 and (args.schedule == "rowstream" or (args.schedule == "auto" and nx * ny * cloths >= 256 * 256))) else
-              "wave_frame_kernel" if (args.schedule == "wave" and 2 <= K <= 8) or (args.schedule == "auto" and 4 <= K <= 8 and nx >= 192 and cloth.rows >= 256) else
+              "wave_frame_kernel" if (args.schedule == "wave" and 2 <= K <= 8) or (args.schedule == "auto" and 4 <= K <= 8 and ((nx >= 192 and cloth.rows >= 256) or (not strips and cloths >= 2 and nx <= 128 and cloths * cloth.rows >= 256 * 148))) else
               "fused_frame_kernel" if args.schedule != "streaming" else "relax_pass_kernel") + suffix
     facts = ncu_facts(wl if args.precision == "f64" and args.schedule == "auto" else None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
