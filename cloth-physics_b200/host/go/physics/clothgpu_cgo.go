@@ -51,7 +51,7 @@ type Cloth struct {
 	gpu     *C.clothgpu
 	// host staging for the render export, reused across frames
 	quads []float32
-	hl   []uint8
+	hl    []uint8
 }
 
 // NewCloth mirrors physics/cloth.go:31-38.  No device work happens until Init.
