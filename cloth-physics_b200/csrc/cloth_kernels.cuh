@@ -81,23 +81,27 @@ __device__ __forceinline__ FrameU<T> pick_frame(const FrameU<T>& u0, const Frame
 
 template <typename T, bool PER_CLOTH>
 __global__ void __launch_bounds__(kStreamThreads)
-    verlet_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth) {
+    verlet_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr) {
     const int e = blockIdx.y;
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     const long long n = (long long)g.held_rows * g.pitch;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int cx = (int)(i % g.pitch);
-    if (cx >= g.nx) return;
-    const long long at = (long long)e * g.cloth_stride + i;
-    T x = P.x[at], y = P.y[at], px = P.px[at], py = P.py[at];
-    uint32_t fl = P.fl[at];
-    particle_update(x, y, px, py, fl, u);
-    P.x[at] = x;
-    P.y[at] = y;
-    P.px[at] = px;
-    P.py[at] = py;
-    P.fl[at] = (uint8_t)fl;
+    ParticleEvents events;
+    if (i < n && (int)(i % g.pitch) < g.nx) {
+        const long long at = (long long)e * g.cloth_stride + i;
+        T x = P.x[at], y = P.y[at], px = P.px[at], py = P.py[at];
+        uint32_t fl = P.fl[at];
+        const uint32_t fl_in = fl;
+        particle_update(x, y, px, py, fl, u);
+        P.x[at] = x;
+        P.y[at] = y;
+        P.px[at] = px;
+        P.py[at] = py;
+        P.fl[at] = (uint8_t)fl;
+        const int gy = g.held_row0 + (int)(i / g.pitch);
+        if (gy >= g.own_row0 && gy < g.own_row0 + g.own_rows) events.note(fl_in, fl);  // ghost rows belong to the neighbour
+    }
+    events.flush(ctr);
 }
 
 // One colour pass over the held rows, in place.  COLOUR: 0 H-even, 1 H-odd, 2 V-even, 3 V-odd
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(kStreamThreads)
 template <typename T, int COLOUR, bool PER_CLOTH>
 __global__ void __launch_bounds__(kStreamThreads)
     relax_pass_kernel(Planes<T> P, Geom g, const FrameU<T> u0, const FrameU<T>* __restrict__ per_cloth,
-                      DevCounters* ctr) {
+                      DevCounters* ctr, int last_sweep) {
     const int e = blockIdx.y;
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     constexpr bool kVertical = COLOUR >= 2;
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(kStreamThreads)
     const unsigned long long v = block_sum_ull(visits);
     const unsigned long long t = block_sum_ull(torn);
     if (threadIdx.x == 0) {
+        // the sticks the frame's last sweep visited and did not tear are the live sticks the next frame starts with
+        if (last_sweep && v != t) atomicAdd(&ctr->live_last, v - t);
         if (v) atomicAdd(&ctr->relaxations, v);
         if (t) {
             atomicAdd(&ctr->torn_total, t);
@@ -521,20 +527,11 @@ __global__ void __launch_bounds__(kStreamThreads)
     }
 }
 
-// ---- row strips over several GPUs: stream-ordered handshake and the explicit edge-row push -----------------------
-// Every strip owns two 32-bit epoch slots in its own memory: slot 0 is written by its upper neighbour, slot 1 by
-// its lower neighbour.  Operation k of a strip (a fused launch, or a push) may start once both neighbours have
-// finished their operation k-1: their stores into my ghost rows have landed, and they no longer read the buffer
-// I am about to write.  Afterwards the strip publishes k in both neighbours' slots.
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
+// ---- row strips over several GPUs: the explicit edge-row push and the whole-operation handshake ---------------------
+// The frame kernels hand-shake by themselves, piece by piece (cloth_types.cuh, StripSync).  The two host-driven strip
+// operations — clothgpu_strip_push after a clothgpu_write_state, and clothgpu_reset — are rare and keep the simple
+// stream-ordered form: a wait kernel (both neighbours have finished operation k-1), the operation, a signal kernel
+// that publishes k+1 in both neighbours' slots.
 __global__ void strip_wait_kernel(const unsigned int* my_slots, int wait_up, int wait_dn, unsigned int need) {
     // epochs only grow; the signed difference tolerates wrap-around
     if (wait_up)

@@ -86,7 +86,7 @@ template <typename T, bool PER_CLOTH, bool DRAG, int RING>
 __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     stream1_frame_kernel(Planes<T> in, Planes<T> out, Geom g, Stream1Plan pl, const FrameU<T> u0,
                          const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr, const PeerOut<T> peer_up,
-                         const PeerOut<T> peer_dn) {
+                         const PeerOut<T> peer_dn, const StripSync ss) {
     using V2 = typename Vec2<T>::type;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -108,6 +108,12 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     const int ra = g.own_row0 + chunk * pl.chunk_rows, rb = min(ra + pl.chunk_rows, own_end);  // owned rows [ra, rb)
     const int rs = max(g.held_row0, ra - 2), re = min(held_end, rb + 2);                       // rows the pipeline reads
     const long long cloth_base = (long long)e * g.cloth_stride;
+    // Attached strips: a chunk that stores rows a neighbour keeps as ghosts (the only chunks that read ghost rows
+    // themselves) waits for that neighbour's epoch first; everybody else starts right away (cloth_types.cuh, StripSync).
+    const bool st_up = ss.my_slots != nullptr && ra < peer_up.row_hi && rb > peer_up.row_lo;
+    const bool st_dn = ss.my_slots != nullptr && ra < peer_dn.row_hi && rb > peer_dn.row_lo;
+    if (st_up) ss.wait(0);
+    if (st_dn) ss.wait(1);
 
     auto load_row = [&](int gy) -> RowRaw<T> {
         RowRaw<T> r;
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     };
 
     unsigned int visits = 0, torn = 0;
+    ParticleEvents events;
     // the row carried from the previous trip (global row r - 1): after V-even, waiting for its V-odd stick
     V2 cE, cO;
     cE.x = cE.y = cO.x = cO.y = T(0);
@@ -257,8 +264,10 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
             fe[q] = rw.fl & 0xffu, fo[q] = rw.fl >> 8;
             T px0 = rw.px.x, px1 = rw.px.y, py0 = rw.py.x, py1 = rw.py.y;
             if (r + q < re && ex_e) {
+                const uint32_t fe_in = fe[q], fo_in = fo[q];
                 particle_update(E[q].x, E[q].y, px0, py0, fe[q], u);
                 if (ex_o) particle_update(O[q].x, O[q].y, px1, py1, fo[q], u);
+                if (own_cols && r + q >= ra && r + q < rb) events.note(fe_in, fe[q]), events.note(fo_in, fo[q]);
                 V2 vpx, vpy;
                 vpx.x = px0, vpx.y = px1, vpy.x = py0, vpy.y = py1;
                 store_prev(r + q, vpx, vpy);
@@ -336,11 +345,23 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     // the last carried row has no row below it when the cloth (strip) ends here
     store_xy(rs + ((re - rs + 1) & ~1) - 1, cE, cO, cfe, cfo);
 
+    if (st_up || st_dn) {  // warp-uniform: my share of the neighbours' ghost rows is written
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            if (st_up) ss.done(0, (unsigned)(min(rb, peer_up.row_hi) - max(ra, peer_up.row_lo)));
+            if (st_dn) ss.done(1, (unsigned)(min(rb, peer_dn.row_hi) - max(ra, peer_dn.row_lo)));
+        }
+    }
+
+    events.flush(ctr);
     for (int o = 16; o > 0; o >>= 1) {
         visits += __shfl_down_sync(FULL, visits, o);
         torn += __shfl_down_sync(FULL, torn, o);
     }
     if (lane == 0) {
+        // one sweep: the sticks visited and not torn are the live sticks the next frame starts with
+        if (visits != torn) atomicAdd(&ctr->live_last, (unsigned long long)(visits - torn));
         if (visits) atomicAdd(&ctr->relaxations, (unsigned long long)visits);
         if (torn) {
             atomicAdd(&ctr->torn_total, (unsigned long long)torn);

@@ -75,11 +75,89 @@ struct FrameU {
     int iterations;
 };
 
-// Device-side counters accumulated by the step kernels (the rest are computed on demand).
+// Device-side counters accumulated by the frame kernels themselves (warp-reduced, one atomic per warp that saw an
+// event), so that clothgpu_get_counters is one small copy instead of a census launch.
 struct DevCounters {
-    unsigned long long relaxations;  // stick visits
+    unsigned long long relaxations;   // stick visits
     unsigned long long torn_total;
-    unsigned long long torn_last;    // reset before each frame
+    unsigned long long torn_last;     // the three *_last slots are zeroed (stream ordered) before each frame
+    unsigned long long live_last;     // sticks the next frame's loop would relax (cloth.go:97), after the last launch
+    unsigned long long hl_last;       // particles highlighted by the frame (particle.go:140-142)
+    unsigned long long pinned_new;    // particles pinned by ctrl-click (particle.go:128-130) since the last census
+    unsigned long long inactive_new;  // particles deactivated by the right button (particle.go:145-149) since then
+};
+
+// What the particle loop changed on the particles a thread owns (events are rare: they need the mouse nearby).
+struct ParticleEvents {
+    unsigned int hl = 0, pinned = 0, holes = 0;
+    __device__ __forceinline__ void note(uint32_t before, uint32_t after) {
+        const uint32_t ev = ((before ^ after) & (CLOTHGPU_FLAG_PIN | CLOTHGPU_FLAG_ACTIVE)) | (after & CLOTHGPU_FLAG_HIGHLIGHT);
+        if (ev) {
+            pinned += ev & 1u;
+            holes += (ev >> 1) & 1u;
+            hl += (ev >> 2) & 1u;
+        }
+    }
+    // all 32 lanes; one atomic per counter and warp, only when something happened
+    __device__ __forceinline__ void flush(DevCounters* ctr) {
+        if (!__any_sync(0xffffffffu, (hl | pinned | holes) != 0u)) return;
+        unsigned int a = hl, b = pinned, c = holes;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+            c += __shfl_down_sync(0xffffffffu, c, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (a) atomicAdd(&ctr->hl_last, (unsigned long long)a);
+            if (b) atomicAdd(&ctr->pinned_new, (unsigned long long)b);
+            if (c) atomicAdd(&ctr->inactive_new, (unsigned long long)c);
+        }
+    }
+};
+
+// ---- row strips over several GPUs: the handshake lives inside the frame kernels ------------------------------------
+// Every strip owns two 32-bit epoch slots in its own memory: slot 0 is written by its upper neighbour, slot 1 by its
+// lower neighbour; epoch k in a slot means "that neighbour has finished the edge work of its operation k-1 ... 0".
+// A piece of work of MY operation k (a CTA's tile, a warp's row chunk) that reads ghost rows or stores into a
+// neighbour's ghost rows first waits until that neighbour's epoch is >= k (`need`): the neighbour's stores of operation
+// k-1 into my ghost rows have landed, and it no longer reads the buffer my stores are about to overwrite.  Pieces that
+// touch neither run without waiting, so the interior of frame f+1 overlaps the neighbours' tail of frame f.
+// When a piece has stored its share of the rows a neighbour keeps as ghosts it fences (system scope) and adds the
+// number of (row, column block) units it covered to a ticket counter in my memory; the piece that completes the
+// operation's quota publishes epoch k+1 in the neighbour's slot (st.release.sys).  Every piece that reads ghost rows
+// also stores peer rows (the neighbour's ghost depth is at least the halo this launch reads), so "all peer stores
+// done" implies "all ghost reads done".
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct StripSync {
+    const unsigned int* my_slots;   // [0] <- upper neighbour, [1] <- lower neighbour; nullptr: not attached
+    unsigned int* peer_slot[2];     // where I publish: the upper neighbour's slot 1, the lower neighbour's slot 0
+    unsigned long long* ticket;     // [2] in my memory, cumulative units stored towards the upper / lower neighbour
+    unsigned long long goal[2];     // value of ticket[side] when this operation's stores towards that side are complete
+    unsigned int need;              // epoch the neighbours must have reached (= operations I have completed)
+
+    // Called by every thread that is about to read ghost rows of / store into the neighbour on `side` (0 up, 1 down).
+    __device__ __forceinline__ void wait(int side) const {
+        // epochs only grow; the signed difference tolerates wrap-around
+        while ((int)(ld_acquire_sys(my_slots + side) - need) < 0) __nanosleep(64);
+    }
+    // Called by ONE thread of a piece after all the piece's threads have fenced (__threadfence_system) their peer stores
+    // and met at a barrier / __syncwarp: accounts `units` towards `side`, publishes the epoch when the quota is complete.
+    __device__ __forceinline__ void done(int side, unsigned int units) const {
+        __threadfence_system();
+        const unsigned long long before = atomicAdd(ticket + side, (unsigned long long)units);
+        if (before + units == goal[side]) {
+            __threadfence_system();
+            st_release_sys(peer_slot[side], need + 1u);
+        }
+    }
 };
 
 // (*particle).update, physics/particle.go:75-181.  `fl` is the particle's flag byte.

@@ -146,7 +146,7 @@ template <typename T, bool PER_CLOTH, bool DRAG, bool PACK = false>
 __global__ void __launch_bounds__(kWaveThreads, 1)
     wave_frame_kernel(Planes<T> in, Planes<T> out, Geom g, WavePlan pl, const FrameU<T> u0,
                       const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr, const PeerOut<T> peer_up,
-                      const PeerOut<T> peer_dn) {
+                      const PeerOut<T> peer_dn, const StripSync ss) {
     using V2 = typename Vec2<T>::type;
     constexpr int TW = kWaveTW, HW = kWaveHW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
 
     const int tid = threadIdx.x;
     unsigned int acc_live = 0, acc_torn = 0, acc_torn_post = 0, acc_extra = 0;
+    ParticleEvents events;
     unsigned int stage_parity = 0;  // entry warps: bit d = phase parity of staging slot d's mbarrier (runs on across chunks)
     if (kWaveTma && tid == kWaveWorkers) {
         for (int d = 0; d < kWaveDepth; ++d) mbar_init(&mbar[d], 1);
@@ -204,6 +205,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     };
     auto slot = [&](int lr) -> int { return lr % RB; };
 
+    // Attached strips: a chunk that stores rows a neighbour keeps as ghosts (the only chunks whose halo reaches into ghost
+    // rows) waits for that neighbour's epoch before it loads — the entry warps do all global traffic — and reports when
+    // its stores are out (cloth_types.cuh, StripSync); every other chunk starts right away.
+    const bool st_up = ss.my_slots != nullptr && ra < peer_up.row_hi && rb > peer_up.row_lo;
+    const bool st_dn = ss.my_slots != nullptr && ra < peer_dn.row_hi && rb > peer_dn.row_lo;
+
     auto owned = [&](int lr, int c) -> bool { return lr >= ly0 && lr < ly1 && c >= lx0 && c < lx1; };
     // a torn stick (after the block states were derived): clear the alive bit of its head's flag byte
     auto tear = [&](int lr, int c, uint32_t alive_bit, int sweep) {
@@ -242,6 +249,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     if (tid >= kWaveWorkers) {
         // =============================== entry warps ===============================================================
         const int et = tid - kWaveWorkers;  // 0..127: the column pair this thread delivers, both rows of a pair
+        if (st_up) ss.wait(0);
+        if (st_dn) ss.wait(1);
         const int c = 2 * et;
         // where local row lr of this thread's column pair lives in HBM, and whether it exists at all
         const int pk_half = PACK ? et >> 6 : 0, pk_cc = PACK ? 2 * (et & 63) : c;
@@ -397,9 +406,11 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     const RowAt ra_ = row_at(lr);
                     if (ra_.ok) {
                         T px0 = vpx.x, px1 = vpx.y, py0 = vpy.x, py1 = vpy.y;
+                        const uint32_t f0_in = f0[row], f1_in = f1[row];
                         particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], u);
                         if (pk_cc + 1 < col_end) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
                         if (owned(lr, c)) {  // the owner of a particle writes its previous position
+                            events.note(f0_in & 0x1fu, f0[row] & 0x1fu), events.note(f1_in & 0x1fu, f1[row] & 0x1fu);
                             const long long at = ra_.at;
                             const int gy = y0 + lr - 2, gx = ox + c;
                             V2 ox2, oy2;
@@ -488,6 +499,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             }
         }
         if (!kWaveTma) cp_async_wait<0>();  // nothing may still be landing in the staging slots when the next chunk starts
+        if (st_up || st_dn) __threadfence_system();  // my stores into the neighbours' ghost rows, before the barrier below
     } else {
         // =============================== worker warps ==============================================================
         // A thread works for the same (at most two) sweep stages and the same column pair during the whole launch, so
@@ -737,19 +749,27 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     }
 
     __syncthreads();  // the ring and the staging slots are reused by the next chunk
+    if (tid == kWaveWorkers) {
+        if (st_up) ss.done(0, (unsigned)(min(rb, peer_up.row_hi) - max(ra, peer_up.row_lo)));
+        if (st_dn) ss.done(1, (unsigned)(min(rb, peer_dn.row_hi) - max(ra, peer_dn.row_lo)));
+    }
     }  // chunks of this CTA
 
     // ---- counters: a stick live when its block state was derived is visited K times unless it tears on the way (then
     // ---- sweep + 1 times, in acc_extra); sticks torn by the entry's H-even pass were visited once -------------------------
     // (per thread the difference may be negative — derivation and tears of one block happen in different threads — so
     //  the sum is formed in signed 64-bit; the grand total is non-negative)
-    long long v = ((long long)acc_live - (long long)acc_torn_post) * K + (long long)acc_extra;
+    events.flush(ctr);
+    int le = (int)acc_live - (int)acc_torn_post;  // live sticks left (signed per thread, see above)
+    long long v = (long long)le * K + (long long)acc_extra;
     unsigned int t = acc_torn;
     for (int o = 16; o > 0; o >>= 1) {
         v += __shfl_down_sync(0xffffffffu, v, o);
         t += __shfl_down_sync(0xffffffffu, t, o);
+        le += __shfl_down_sync(0xffffffffu, le, o);
     }
     if ((tid & 31) == 0) {
+        if (le) atomicAdd(&ctr->live_last, (unsigned long long)(long long)le);  // (two's complement: negative partial sums cancel)
         if (v) atomicAdd(&ctr->relaxations, (unsigned long long)v);
         if (t) {
             atomicAdd(&ctr->torn_total, (unsigned long long)t);

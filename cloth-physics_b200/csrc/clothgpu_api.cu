@@ -16,6 +16,7 @@
 
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
+#include "cloth_selftest.cuh"
 #include "cloth_stream1.cuh"
 #include "cloth_wave.cuh"
 #include "frame_fold.h"
@@ -67,9 +68,20 @@ struct clothgpu {
     void* PY[2] = {nullptr, nullptr};
     uint8_t* FL[2] = {nullptr, nullptr};
     int cur_pos = 0, cur_prev = 0;
-    DevCounters* ctr = nullptr;        // [0] totals; torn slots live in torn2
-    unsigned long long* torn2 = nullptr;  // torn count of even / odd frames
-    unsigned long long* census = nullptr; // 5 values
+    DevCounters* ctr = nullptr;           // accumulated by the frame kernels (cloth_types.cuh)
+    unsigned long long* census = nullptr; // 5 values, written by count_kernel
+    // Pinned staging for clothgpu_get_counters: [0] a DevCounters, then the 5 census values.
+    unsigned char* ctr_host = nullptr;
+    // The census (a full pass over the flag bytes) runs only when the flags changed behind the kernels' back — create,
+    // reset, write_state; from then on the frame kernels keep the deltas (DevCounters) and get_counters is one 56-byte copy.
+    bool census_valid = false;
+    struct {
+        unsigned long long live = 0, alive = 0, pinned = 0, inactive = 0, highlighted = 0;
+        unsigned long long torn_total = 0;  // DevCounters::torn_total when the census was taken
+        uint64_t frames = 0;                // c->frames when the census was taken
+    } base;
+    int last_sched = -1;                  // what the last step resolved to (clothgpu_last_schedule)
+    const char* last_kernel = nullptr;
     void* frames_dev = nullptr;        // per-cloth FrameU array (ensemble input)
     void* frames_host = nullptr;       // pinned staging for the above
     cudaEvent_t frames_copied = nullptr;
@@ -96,6 +108,8 @@ struct clothgpu {
     size_t off_plane[10] = {0};  // X0 X1 Y0 Y1 PX0 PX1 PY0 PY1 FL0 FL1
     size_t off_slots = 0;
     unsigned int* slots = nullptr;  // [0] written by my upper neighbour, [1] by my lower neighbour
+    unsigned long long* ticket = nullptr;      // [2] next to the slots: units stored towards the upper / lower neighbour
+    unsigned long long ticket_goal[2] = {0, 0};  // cumulative quota of all operations issued so far
     struct Link {
         bool on = false;
         bool ipc = false;      // base came from cudaIpcOpenMemHandle (must be closed)
@@ -232,7 +246,30 @@ PeerOut<T> peer_out(const clothgpu* c, int side, int pos, int prev) {
 
 bool attached(const clothgpu* c) { return c->link[0].on || c->link[1].on; }
 
-// Operation k may start once both neighbours finished operation k-1 (cloth_kernels.cuh).
+// The in-kernel handshake of one frame-kernel launch (cloth_types.cuh, StripSync).  `columns` = how many pieces of
+// work share one row of the cloth (column windows / bands / tile columns, times the ensemble): a neighbour's ghost
+// copy of my rows [row_lo, row_hi) is complete when rows x columns units have been reported.  Counts as one strip
+// operation (the epoch advances).
+StripSync make_sync(clothgpu* c, long long columns) {
+    StripSync s{};
+    if (!attached(c)) return s;
+    s.my_slots = c->slots;
+    s.ticket = c->ticket;
+    s.need = c->epoch;
+    for (int side = 0; side < 2; ++side) {
+        const clothgpu::Link& l = c->link[side];
+        if (!l.on) continue;
+        // I am the LOWER neighbour of my upper neighbour: its slot 1; and the UPPER neighbour of my lower one: its slot 0
+        s.peer_slot[side] = (unsigned int*)(l.base + l.off_slots) + (side == 0 ? 1 : 0);
+        c->ticket_goal[side] += (unsigned long long)(l.row_hi - l.row_lo) * (unsigned long long)columns;
+        s.goal[side] = c->ticket_goal[side];
+    }
+    c->epoch++;
+    return s;
+}
+
+// Host-driven strip operations (push, reset): operation k may start once both neighbours finished operation k-1
+// (cloth_kernels.cuh).  The frame kernels do this themselves, piece by piece (make_sync).
 int strip_begin_op(clothgpu* c) {
     if (!attached(c)) return CLOTHGPU_OK;
     strip_wait_kernel<<<1, 1, 0, c->stream>>>(c->slots, c->link[0].on, c->link[1].on, c->epoch);
@@ -270,12 +307,12 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     Planes<T> out = planes<T>(c, nxt, nprev);
     // strips: the neighbours run the same operation sequence, so their buffer indices equal mine
     const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
-    if (int rc = strip_begin_op(c)) return rc;
+    const StripSync ss = make_sync(c, (long long)pl.tiles_x * c->g.ensemble);
     dim3 grid(pl.tiles_x, pl.tiles_y, c->g.ensemble);
     auto go = [&](auto kernel, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return e;
-        kernel<<<grid, threads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr, pup, pdn);
+        kernel<<<grid, threads, smem, c->stream>>>(in, out, c->g, pl, u, per_cloth, c->ctr, pup, pdn, ss);
         return cudaSuccess;
     };
     // PER_CLOTH: every cloth has its own frame block (buttons differ), so the tear test stays in.  Otherwise the
@@ -313,7 +350,9 @@ int launch_fused(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth, in
     c->launches++;
     c->cur_pos = nxt;
     if (do_verlet) c->cur_prev ^= 1;
-    return strip_end_op(c);
+    c->last_kernel = std::is_same<T, double>::value ? (pc ? "fused_frame_kernel<double,PER_CLOTH>" : drag ? "fused_frame_kernel<double,DRAG>" : "fused_frame_kernel<double>")
+                                                    : (pc ? "fused_frame_kernel<float,PER_CLOTH>" : drag ? "fused_frame_kernel<float,DRAG>" : "fused_frame_kernel<float>");
+    return CLOTHGPU_OK;
 }
 
 // One sweep per frame (the reference's own semantics): the register-streaming kernel, one pass over HBM.
@@ -355,7 +394,7 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
     Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
     Planes<T> out = planes<T>(c, nxt, nprev);
     const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
-    if (int rc = strip_begin_op(c)) return rc;
+    const StripSync ss = make_sync(c, (long long)pl.windows * g.ensemble);
     const unsigned blocks = (unsigned)((pl.tasks + kS1Threads / 32 - 1) / (kS1Threads / 32));
     const bool pc = per_cloth != nullptr;
     const bool drag = pc || (u.buttons & CLOTHGPU_MOUSE_DRAGGING);
@@ -364,7 +403,7 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kernel<<<blocks, kS1Threads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+        kernel<<<blocks, kS1Threads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn, ss);
         return cudaSuccess;
     };
     auto pick = [&](auto ring) -> cudaError_t {
@@ -382,7 +421,9 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
     c->launches++;
     c->cur_pos = nxt;
     c->cur_prev = nprev;
-    return strip_end_op(c);
+    c->last_kernel = std::is_same<T, double>::value ? (pc ? "stream1_frame_kernel<double,PER_CLOTH>" : drag ? "stream1_frame_kernel<double,DRAG>" : "stream1_frame_kernel<double>")
+                                                    : (pc ? "stream1_frame_kernel<float,PER_CLOTH>" : drag ? "stream1_frame_kernel<float,DRAG>" : "stream1_frame_kernel<float>");
+    return CLOTHGPU_OK;
 }
 
 // 2..8 sweeps per frame: the wavefront kernel (cloth_wave.cuh).
@@ -442,14 +483,14 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     Planes<T> in = planes<T>(c, c->cur_pos, c->cur_prev);
     Planes<T> out = planes<T>(c, nxt, nprev);
     const PeerOut<T> pup = peer_out<T>(c, 0, nxt, nprev), pdn = peer_out<T>(c, 1, nxt, nprev);
-    if (int rc = strip_begin_op(c)) return rc;
+    const StripSync ss = make_sync(c, pl.columns);
     dim3 grid(n_ctas);
     const bool pc = per_cloth != nullptr;
     const bool drag = pc || (u.buttons & CLOTHGPU_MOUSE_DRAGGING);
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return e;
-        kernel<<<grid, kWaveThreads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn);
+        kernel<<<grid, kWaveThreads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn, ss);
         return cudaSuccess;
     };
     if (pc)
@@ -464,7 +505,12 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     c->launches++;
     c->cur_pos = nxt;
     c->cur_prev = nprev;
-    return strip_end_op(c);
+    c->last_kernel = std::is_same<T, double>::value
+                         ? (pc ? "wave_frame_kernel<double,PER_CLOTH>" : pl.pack ? (drag ? "wave_frame_kernel<double,DRAG,PACK>" : "wave_frame_kernel<double,PACK>")
+                                                                                 : drag ? "wave_frame_kernel<double,DRAG>" : "wave_frame_kernel<double>")
+                         : (pc ? "wave_frame_kernel<float,PER_CLOTH>" : pl.pack ? (drag ? "wave_frame_kernel<float,DRAG,PACK>" : "wave_frame_kernel<float,PACK>")
+                                                                                : drag ? "wave_frame_kernel<float,DRAG>" : "wave_frame_kernel<float>");
+    return CLOTHGPU_OK;
 }
 
 template <typename T>
@@ -480,13 +526,14 @@ int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth
     dim3 gv((unsigned)((nv + kStreamThreads - 1) / kStreamThreads), g.ensemble);
     auto run = [&](auto pcflag) {
         constexpr bool PC = decltype(pcflag)::value;
-        verlet_kernel<T, PC><<<gp, kStreamThreads, 0, c->stream>>>(P, g, u, fr);
+        verlet_kernel<T, PC><<<gp, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
         c->launches++;
         for (int it = 0; it < u.iterations; ++it) {
-            relax_pass_kernel<T, 0, PC><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-            relax_pass_kernel<T, 1, PC><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-            relax_pass_kernel<T, 2, PC><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
-            relax_pass_kernel<T, 3, PC><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr);
+            const int last = it + 1 == u.iterations;
+            relax_pass_kernel<T, 0, PC><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr, last);
+            relax_pass_kernel<T, 1, PC><<<gh, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr, last);
+            relax_pass_kernel<T, 2, PC><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr, last);
+            relax_pass_kernel<T, 3, PC><<<gv, kStreamThreads, 0, c->stream>>>(P, g, u, fr, c->ctr, last);
             c->launches += 4;
         }
     };
@@ -495,6 +542,7 @@ int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth
     else
         run(std::false_type{});
     CU_TRY(cudaGetLastError());
+    c->last_kernel = std::is_same<T, double>::value ? "verlet_kernel<double> + relax_pass_kernel<double> x 4K" : "verlet_kernel<float> + relax_pass_kernel<float> x 4K";
     return CLOTHGPU_OK;
 }
 
@@ -537,7 +585,9 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         CU_TRY(cudaEventRecord(c->frames_copied, c->stream));
         dev_frames = (const FrameU<T>*)c->frames_dev;
     }
-    CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, sizeof(unsigned long long), c->stream));
+    // torn_last, live_last, hl_last: the frame kernels accumulate this frame's values (cloth_types.cuh, DevCounters)
+    static_assert(offsetof(DevCounters, hl_last) == offsetof(DevCounters, torn_last) + 2 * sizeof(unsigned long long), "layout");
+    CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, 3 * sizeof(unsigned long long), c->stream));
     int sched = c->schedule;
     if (sched == CLOTHGPU_SCHED_AUTO) {
         // One sweep: the row-streaming kernel, unless the cloth is too small to feed enough independent warps.
@@ -573,12 +623,16 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         rc = CLOTHGPU_OK;
         while (left > 0 && rc == CLOTHGPU_OK) {
             const int k = std::min(left, c->sweeps_per_launch);
+            if (!first) CU_TRY(cudaMemsetAsync(&c->ctr->live_last, 0, sizeof(unsigned long long), c->stream));  // the last launch's count stands
             rc = launch_fused<T>(c, u0, dev_frames, k, first);
             first = 0;
             left -= k;
         }
     }
-    if (rc == CLOTHGPU_OK) c->frames++;
+    if (rc == CLOTHGPU_OK) {
+        c->frames++;
+        c->last_sched = sched;
+    }
     return rc;
 }
 
@@ -589,6 +643,11 @@ int step_dispatch(clothgpu* c, const clothgpu_frame* frames, int count, bool per
 
 template <typename T>
 int init_state(clothgpu* c, int pos_x, int pos_y) {
+    // Attached strips: Reset is a strip operation like a frame.  The init kernel rewrites my ghost rows too, so the
+    // neighbours' stores of the previous operation into them must have landed first (strip_begin_op), and the
+    // neighbours may only store into my ghost rows again once the init is done (strip_end_op).  Every strip resets at
+    // the same point of the common call sequence, so all of them are back on buffer 0 afterwards.
+    if (int rc = strip_begin_op(c)) return rc;
     c->cur_pos = c->cur_prev = 0;
     Planes<T> P = planes<T>(c, 0, 0);
     init_grid_kernel<T><<<c->sm_count * 8, 256, 0, c->stream>>>(P, c->g, c->ny, c->desc.spacing, pos_x,
@@ -597,7 +656,8 @@ int init_state(clothgpu* c, int pos_x, int pos_y) {
     c->launches++;
     CU_TRY(cudaMemsetAsync(c->ctr, 0, sizeof(DevCounters), c->stream));
     c->frames = 0;
-    return CLOTHGPU_OK;
+    c->census_valid = false;
+    return strip_end_op(c);
 }
 
 void free_all(clothgpu* c) {
@@ -608,6 +668,7 @@ void free_all(clothgpu* c) {
     cudaFree(c->slab);
     cudaFree(c->ctr);
     cudaFree(c->census);
+    cudaFreeHost(c->ctr_host);
     cudaFree(c->frames_dev);
     cudaFreeHost(c->frames_host);
     cudaFree(c->seg_counts);
@@ -784,11 +845,16 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
                 c->FL[i] = (uint8_t*)(b + c->off_plane[8 + i]);
             }
             c->slots = (unsigned int*)(b + c->off_slots);
+            c->ticket = (unsigned long long*)(b + c->off_slots + 64);
         }
     }
     alloc((void**)&c->ctr, sizeof(DevCounters));
     alloc((void**)&c->census, 5 * sizeof(unsigned long long));
     alloc((void**)&c->seg_total, sizeof(unsigned long long));
+    if (rc == CLOTHGPU_OK) {
+        cudaError_t ee = cudaMallocHost((void**)&c->ctr_host, sizeof(DevCounters) + 5 * sizeof(unsigned long long));
+        if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(ee));
+    }
     const size_t fbytes = sizeof(FrameU<double>) * (size_t)ensemble;
     alloc(&c->frames_dev, fbytes);
     if (rc == CLOTHGPU_OK) {
@@ -961,7 +1027,11 @@ int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const doub
     }
     if (flags) {
         // keep the invariants Init establishes: no stick past the last column / last row
+        // only the five CLOTHGPU_FLAG_* bits are state (the packed-ensemble schedule parks alive bits in the spare ones
+        // while a frame is in flight; a stray bit there must not turn into a stick)
         std::vector<uint8_t> fl(flags, flags + n);
+        for (size_t i = 0; i < n; ++i) fl[i] &= 0x1f;
+        c->census_valid = false;
         for (int r = 0; r < g.own_rows; ++r) {
             fl[(size_t)r * g.nx + g.nx - 1] &= (uint8_t)~CLOTHGPU_FLAG_ALIVE_H;
             if (g.own_row0 + r == c->ny - 1)
@@ -1115,29 +1185,46 @@ int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
     if (int rc = check_handle(c)) return rc;
     if (!out) return fail(CLOTHGPU_ERR_INVALID, "null out");
     const Geom& g = c->g;
-    CU_TRY(cudaMemsetAsync(c->census, 0, 5 * sizeof(unsigned long long), c->stream));
-    const long long chunks = (long long)g.own_rows * g.pitch / 16;
-    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((chunks + kStreamThreads - 1) / kStreamThreads, c->sm_count * 4)), g.ensemble);
-    if (c->precision == CLOTHGPU_F32)
-        count_kernel<float><<<grid, kStreamThreads, 0, c->stream>>>(planes<float>(c, c->cur_pos, c->cur_prev), g, c->census);
-    else
-        count_kernel<double><<<grid, kStreamThreads, 0, c->stream>>>(planes<double>(c, c->cur_pos, c->cur_prev), g, c->census);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
-    unsigned long long h5[5];
-    DevCounters hc;
-    CU_TRY(cudaMemcpyAsync(h5, c->census, sizeof h5, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaMemcpyAsync(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    DevCounters* hc = (DevCounters*)c->ctr_host;
+    unsigned long long* h5 = (unsigned long long*)(c->ctr_host + sizeof(DevCounters));
+    const bool census = !c->census_valid;
+    if (census) {
+        // the flag bytes changed behind the frame kernels' back (create, reset, write_state): count them once
+        CU_TRY(cudaMemsetAsync(c->census, 0, 5 * sizeof(unsigned long long), c->stream));
+        const long long chunks = (long long)g.own_rows * g.pitch / 16;
+        dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((chunks + kStreamThreads - 1) / kStreamThreads, c->sm_count * 4)), g.ensemble);
+        if (c->precision == CLOTHGPU_F32)
+            count_kernel<float><<<grid, kStreamThreads, 0, c->stream>>>(planes<float>(c, c->cur_pos, c->cur_prev), g, c->census);
+        else
+            count_kernel<double><<<grid, kStreamThreads, 0, c->stream>>>(planes<double>(c, c->cur_pos, c->cur_prev), g, c->census);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        CU_TRY(cudaMemcpyAsync(h5, c->census, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        // the census includes everything the queued frames did: their deltas start again from zero
+        static_assert(offsetof(DevCounters, inactive_new) == offsetof(DevCounters, pinned_new) + sizeof(unsigned long long), "layout");
+        CU_TRY(cudaMemsetAsync(&c->ctr->pinned_new, 0, 2 * sizeof(unsigned long long), c->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(hc, c->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    h5[3] = (unsigned long long)g.nx * g.own_rows * g.ensemble - h5[3];  // the kernel counts ACTIVE particles
+    if (census) {
+        c->base.live = h5[0];
+        c->base.alive = h5[1];
+        c->base.pinned = h5[2];
+        c->base.inactive = (unsigned long long)g.nx * g.own_rows * g.ensemble - h5[3];  // the kernel counts ACTIVE particles
+        c->base.highlighted = h5[4];
+        c->base.torn_total = hc->torn_total;
+        c->base.frames = c->frames;
+        c->census_valid = true;
+    }
+    const bool stepped = c->frames > c->base.frames;  // frames since the census: the kernels' own counts stand
     out->frames = c->frames;
-    out->live_sticks = h5[0];
-    out->alive_sticks = h5[1];
-    out->pinned = h5[2];
-    out->inactive = h5[3];
-    out->highlighted = h5[4];
-    out->torn_last = hc.torn_last;
-    out->relaxations = hc.relaxations;
+    out->live_sticks = stepped ? hc->live_last : c->base.live;
+    out->alive_sticks = c->base.alive - (hc->torn_total - c->base.torn_total);
+    out->pinned = c->base.pinned + hc->pinned_new;
+    out->inactive = c->base.inactive + hc->inactive_new;
+    out->highlighted = stepped ? hc->hl_last : c->base.highlighted;
+    out->torn_last = hc->torn_last;
+    out->relaxations = hc->relaxations;
     return CLOTHGPU_OK;
 }
 
@@ -1313,6 +1400,61 @@ int clothgpu_launch_count(clothgpu* c, uint64_t* launches) {
     if (!c || !launches) return fail(CLOTHGPU_ERR_INVALID, "null argument");
     *launches = c->launches;
     return CLOTHGPU_OK;
+}
+
+int clothgpu_last_schedule(clothgpu* c, int32_t* schedule, const char** kernel_name) {
+    if (!c) return fail(CLOTHGPU_ERR_INVALID, "null handle");
+    if (c->last_sched < 0 || !c->last_kernel) return fail(CLOTHGPU_ERR_STATE, "no step has been issued yet");
+    if (schedule) *schedule = c->last_sched;
+    if (kernel_name) *kernel_name = c->last_kernel;
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_selftest_stickmath(int32_t device, uint64_t seed, uint64_t samples, const double* s_list, size_t n_list,
+                                clothgpu_stickmath_report* report) {
+    if (!report) return fail(CLOTHGPU_ERR_INVALID, "null report");
+    static_assert(sizeof(StickMathReport) == sizeof(clothgpu_stickmath_report), "report layouts must agree");
+    memset(report, 0, sizeof *report);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CLOTHGPU_ERR_NODEVICE, "no CUDA device (%s); clothgpu has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(CLOTHGPU_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(CLOTHGPU_ERR_NODEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    CU_TRY(cudaSetDevice(device));
+    for (size_t i = 0; i < n_list; ++i)
+        if (!s_list || !(s_list[i] >= 1.0) || !(s_list[i] < 0x1p900))
+            return fail(CLOTHGPU_ERR_INVALID, "s_list[%zu] is outside [1, 2^900)", i);
+    StickMathReport* d_rep = nullptr;
+    double* d_list = nullptr;
+    CU_TRY(cudaMalloc((void**)&d_rep, sizeof(StickMathReport)));
+    int rc = CLOTHGPU_OK;
+    auto step = [&](cudaError_t ee, const char* what) {
+        if (rc == CLOTHGPU_OK && ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ee));
+    };
+    step(cudaMemset(d_rep, 0, sizeof(StickMathReport)), "cudaMemset");
+    const double gain = 0.35;  // physics/constraint.go:42
+    if (rc == CLOTHGPU_OK && samples) {
+        stickmath_random_kernel<<<prop.multiProcessorCount * 8, 256>>>(seed, samples, gain, d_rep);
+        step(cudaGetLastError(), "stickmath_random_kernel");
+    }
+    if (rc == CLOTHGPU_OK && n_list) {
+        step(cudaMalloc((void**)&d_list, n_list * sizeof(double)), "cudaMalloc");
+        if (rc == CLOTHGPU_OK) step(cudaMemcpy(d_list, s_list, n_list * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy");
+        if (rc == CLOTHGPU_OK) {
+            const unsigned blocks = (unsigned)std::min<size_t>((n_list * 64 + 255) / 256, (size_t)prop.multiProcessorCount * 8);
+            stickmath_list_kernel<<<blocks, 256>>>(d_list, n_list, gain, d_rep);
+            step(cudaGetLastError(), "stickmath_list_kernel");
+        }
+    }
+    step(cudaDeviceSynchronize(), "self-test kernels");
+    if (rc == CLOTHGPU_OK) step(cudaMemcpy(report, d_rep, sizeof *report, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    cudaFree(d_list);
+    cudaFree(d_rep);
+    return rc;
 }
 
 const char* clothgpu_last_error(void) { return g_last_error.c_str(); }

@@ -24,6 +24,7 @@ EXPORTS = [
     "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_read_quads_f32", "clothgpu_compact_segments",
     "clothgpu_get_counters",
     "clothgpu_halo_region", "clothgpu_strip_export", "clothgpu_strip_attach", "clothgpu_strip_push", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
+    "clothgpu_last_schedule", "clothgpu_selftest_stickmath",
     "clothgpu_last_error", "clothgpu_version",
 ]
 
@@ -74,6 +75,9 @@ def lib():
         L.clothgpu_set_stream.argtypes = [vp, vp]
         L.clothgpu_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.clothgpu_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.clothgpu_last_schedule.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]
+        L.clothgpu_selftest_stickmath.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, dp, C.c_size_t,
+                                                  C.POINTER(_abi.StickMathReport)]
         L.clothgpu_last_error.restype = C.c_char_p
         L.clothgpu_version.restype = C.c_char_p
         _lib = L
@@ -94,6 +98,15 @@ def frame_array(frames):
     for i, f in enumerate(frames):
         C.memmove(C.byref(arr[i]), C.byref(f), C.sizeof(Frame))
     return arr
+
+
+def selftest_stickmath(samples=0, s_list=None, seed=1, device=0):
+    """Device self-test of the binary64 stick arithmetic against sqrt.rn / div.rn (include/clothgpu.h)."""
+    rep = _abi.StickMathReport()
+    arr = None if s_list is None else np.ascontiguousarray(s_list, np.float64)
+    _check(lib().clothgpu_selftest_stickmath(device, seed, samples, _p(arr, C.c_double), 0 if arr is None else arr.size,
+                                             C.byref(rep)))
+    return rep.as_dict()
 
 
 class Cloth:
@@ -233,6 +246,12 @@ class Cloth:
         ms = C.c_float()
         _check(self._L.clothgpu_last_step_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_schedule(self):
+        """(clothgpu_schedule, kernel name) the last step actually ran."""
+        sched, name = C.c_int32(), C.c_char_p()
+        _check(self._L.clothgpu_last_schedule(self._h, C.byref(sched), C.byref(name)))
+        return sched.value, name.value.decode()
 
     def launch_count(self):
         n = C.c_uint64()

@@ -60,6 +60,14 @@ class Counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class StickMathReport(C.Structure):
+    _fields_ = [("tested", C.c_uint64), ("mismatches", C.c_uint64)] + [(n, C.c_double) for n in (
+        "first_s", "first_L", "got_dist", "want_dist", "got_mul", "want_mul")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class Info(C.Structure):
     _fields_ = [
         ("nx", C.c_int32), ("ny", C.c_int32), ("row0", C.c_int32), ("rows", C.c_int32),

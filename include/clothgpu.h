@@ -278,6 +278,26 @@ CLOTHGPU_API int clothgpu_last_step_ms(clothgpu* c, float* ms);
 /* Number of kernel launches issued by this handle since create. */
 CLOTHGPU_API int clothgpu_launch_count(clothgpu* c, uint64_t* launches);
 
+/* The schedule the last clothgpu_step / step_n / step_each actually ran (AUTO and the fall-backs resolved): a
+ * clothgpu_schedule value, and the name of the frame kernel (static string, e.g. "stream1_frame_kernel<double,DRAG>").
+ * Either pointer may be NULL.  CLOTHGPU_ERR_STATE before the first step. */
+CLOTHGPU_API int clothgpu_last_schedule(clothgpu* c, int32_t* schedule, const char** kernel_name);
+
+/* Device self-test of the binary64 stick arithmetic (test hook; no reference counterpart).  Every fast kernel derives
+ * sqrt(s), (L - d)/d and L/d of physics/constraint.go:28,41-42 from one reciprocal-square-root seed; this runs that
+ * expansion against the device's own IEEE sqrt.rn.f64 / div.rn.f64 on `samples` pseudo-random stretched sticks (rest
+ * length 1..64, squared length up to 2^61, random mantissas; seed selects the sequence) and on every squared length of
+ * `s_list` (n_list entries, may be NULL) paired with every rest length 1..64 that leaves it stretched.  The report
+ * counts the compared pairs and the mismatches (0 expected) and holds the first mismatching operands. */
+typedef struct clothgpu_stickmath_report {
+    uint64_t tested;
+    uint64_t mismatches;
+    double first_s, first_L;
+    double got_dist, want_dist, got_mul, want_mul;
+} clothgpu_stickmath_report;
+CLOTHGPU_API int clothgpu_selftest_stickmath(int32_t device, uint64_t seed, uint64_t samples, const double* s_list,
+                                size_t n_list, clothgpu_stickmath_report* report);
+
 CLOTHGPU_API const char* clothgpu_last_error(void);
 CLOTHGPU_API const char* clothgpu_version(void);
 

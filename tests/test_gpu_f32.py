@@ -1,9 +1,8 @@
 """The optional binary32 mode (BASELINE.json: "stored as float64 for parity with an optional fp32 mode") against the oracle
 run in binary32 (oracle/cloth_oracle.c instantiates its implementation for float as well).
 
-Written at the end of round 1 when the GPU budget was spent, so it has never run: non-strict xfail keeps an unexpected
-result from turning the suite red; the first GPU run decides (XPASS = the mode is bit-exact, remove the marker; XFAIL =
-look at the report).  Until then the F32 mode is covered by the bench (`bench.py --precision f32`) only.
+First run on the round-1 driver box (GPUTEST_r01.json: XPASS on every case); the xfail marker it carried until then is
+gone, so a binary32 mismatch now fails the suite.
 """
 import numpy as np
 import pytest
@@ -14,8 +13,7 @@ from clothgpu._abi import MOUSE_DRAGGING, SCHED_FUSED, SCHED_ROWSTREAM, SCHED_ST
 
 from test_gpu_parity import assert_same_state, random_state
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="never run: written after the round's GPU budget was spent")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("nx,ny,K,schedule", [(171, 36, 1, SCHED_ROWSTREAM), (171, 36, 1, SCHED_FUSED), (130, 131, 3, SCHED_FUSED),
