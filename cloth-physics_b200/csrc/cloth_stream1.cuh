@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     const long long cloth_base = (long long)e * g.cloth_stride;
     // Attached strips: a chunk that stores rows a neighbour keeps as ghosts (the only chunks that read ghost rows
     // themselves) waits for that neighbour's epoch first; everybody else starts right away (cloth_types.cuh, StripSync).
-    const bool st_up = ss.my_slots != nullptr && ra < peer_up.row_hi && rb > peer_up.row_lo;
-    const bool st_dn = ss.my_slots != nullptr && ra < peer_dn.row_hi && rb > peer_dn.row_lo;
+    const bool st_up = ss.on() && ra < peer_up.row_hi && rb > peer_up.row_lo;
+    const bool st_dn = ss.on() && ra < peer_dn.row_hi && rb > peer_dn.row_lo;
     if (st_up) ss.wait(0);
     if (st_dn) ss.wait(1);
 
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                 const uint32_t fe_in = fe[q], fo_in = fo[q];
                 particle_update(E[q].x, E[q].y, px0, py0, fe[q], u);
                 if (ex_o) particle_update(O[q].x, O[q].y, px1, py1, fo[q], u);
-                if (own_cols && r + q >= ra && r + q < rb) events.note(fe_in, fe[q]), events.note(fo_in, fo[q]);
+                if (own_cols && r + q >= ra && r + q < rb) events.note2(fe_in, fe[q], fo_in, fo[q]);
                 V2 vpx, vpy;
                 vpx.x = px0, vpx.y = px1, vpy.x = py0, vpy.y = py1;
                 store_prev(r + q, vpx, vpy);

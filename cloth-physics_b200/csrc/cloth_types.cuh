@@ -91,11 +91,26 @@ struct DevCounters {
 struct ParticleEvents {
     unsigned int hl = 0, pinned = 0, holes = 0;
     __device__ __forceinline__ void note(uint32_t before, uint32_t after) {
+#ifdef CLOTH_NO_EVENTS  // timing experiment only (counters wrong)
+        return;
+#endif
         const uint32_t ev = ((before ^ after) & (CLOTHGPU_FLAG_PIN | CLOTHGPU_FLAG_ACTIVE)) | (after & CLOTHGPU_FLAG_HIGHLIGHT);
         if (ev) {
             pinned += ev & 1u;
             holes += (ev >> 1) & 1u;
             hl += (ev >> 2) & 1u;
+        }
+    }
+    // the (even, odd) column pair a lane owns: one combined test on the common path
+    __device__ __forceinline__ void note2(uint32_t before0, uint32_t after0, uint32_t before1, uint32_t after1) {
+#ifdef CLOTH_NO_EVENTS
+        return;
+#endif
+        const uint32_t any = (((before0 ^ after0) | (before1 ^ after1)) & (CLOTHGPU_FLAG_PIN | CLOTHGPU_FLAG_ACTIVE)) |
+                             ((after0 | after1) & CLOTHGPU_FLAG_HIGHLIGHT);
+        if (any) {
+            note(before0, after0);
+            note(before1, after1);
         }
     }
     // all 32 lanes; one atomic per counter and warp, only when something happened
@@ -143,6 +158,11 @@ struct StripSync {
     unsigned long long goal[2];     // value of ticket[side] when this operation's stores towards that side are complete
     unsigned int need;              // epoch the neighbours must have reached (= operations I have completed)
 
+#ifdef CLOTH_NO_STRIPSYNC  // timing experiment only (attached strips unsynchronised)
+    __device__ __forceinline__ bool on() const { return false; }
+#else
+    __device__ __forceinline__ bool on() const { return my_slots != nullptr; }
+#endif
     // Called by every thread that is about to read ghost rows of / store into the neighbour on `side` (0 up, 1 down).
     __device__ __forceinline__ void wait(int side) const {
         // epochs only grow; the signed difference tolerates wrap-around

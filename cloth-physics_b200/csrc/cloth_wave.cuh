@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     // Attached strips: a chunk that stores rows a neighbour keeps as ghosts (the only chunks whose halo reaches into ghost
     // rows) waits for that neighbour's epoch before it loads — the entry warps do all global traffic — and reports when
     // its stores are out (cloth_types.cuh, StripSync); every other chunk starts right away.
-    const bool st_up = ss.my_slots != nullptr && ra < peer_up.row_hi && rb > peer_up.row_lo;
-    const bool st_dn = ss.my_slots != nullptr && ra < peer_dn.row_hi && rb > peer_dn.row_lo;
+    const bool st_up = ss.on() && ra < peer_up.row_hi && rb > peer_up.row_lo;
+    const bool st_dn = ss.on() && ra < peer_dn.row_hi && rb > peer_dn.row_lo;
 
     auto owned = [&](int lr, int c) -> bool { return lr >= ly0 && lr < ly1 && c >= lx0 && c < lx1; };
     // a torn stick (after the block states were derived): clear the alive bit of its head's flag byte
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                         particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], u);
                         if (pk_cc + 1 < col_end) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
                         if (owned(lr, c)) {  // the owner of a particle writes its previous position
-                            events.note(f0_in & 0x1fu, f0[row] & 0x1fu), events.note(f1_in & 0x1fu, f1[row] & 0x1fu);
+                            events.note2(f0_in & 0x1fu, f0[row] & 0x1fu, f1_in & 0x1fu, f1[row] & 0x1fu);
                             const long long at = ra_.at;
                             const int gy = y0 + lr - 2, gx = ox + c;
                             V2 ox2, oy2;

@@ -15,6 +15,8 @@ from ._abi import *  # noqa: F401,F403  (constants)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "csrc", "libclothgpu.so"))
+if os.environ.get("CLOTHGPU_LIB"):      # A/B timing of another build of the same library (tools/ab_time.sh); never a fallback
+    LIB_PATH = os.path.abspath(os.environ["CLOTHGPU_LIB"])
 
 # Every symbol include/clothgpu.h declares.
 EXPORTS = [
@@ -75,9 +77,10 @@ def lib():
         L.clothgpu_set_stream.argtypes = [vp, vp]
         L.clothgpu_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.clothgpu_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
-        L.clothgpu_last_schedule.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]
-        L.clothgpu_selftest_stickmath.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, dp, C.c_size_t,
-                                                  C.POINTER(_abi.StickMathReport)]
+        if hasattr(L, "clothgpu_last_schedule"):    # (absent from the round-1 build used for A/B timing)
+            L.clothgpu_last_schedule.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]
+            L.clothgpu_selftest_stickmath.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, dp, C.c_size_t,
+                                                      C.POINTER(_abi.StickMathReport)]
         L.clothgpu_last_error.restype = C.c_char_p
         L.clothgpu_version.restype = C.c_char_p
         _lib = L
@@ -208,6 +211,13 @@ class Cloth:
         _check(self._L.clothgpu_read_quads_f32(self._h, cloth, C.c_float(line_width), _p(quads, C.c_float),
                                                _p(hl, C.c_uint8), cap, C.byref(n)))
         return quads[:n.value], hl[:n.value]
+
+    def read_quads_into(self, quads_ptr, hl_ptr, cap, cloth=0, line_width=0.6):
+        """clothgpu_read_quads_f32 into caller-owned (e.g. pinned) host memory given as raw addresses; returns n."""
+        n = C.c_size_t(0)
+        _check(self._L.clothgpu_read_quads_f32(self._h, cloth, C.c_float(line_width), C.cast(quads_ptr, C.POINTER(C.c_float)),
+                                               C.cast(hl_ptr, C.POINTER(C.c_uint8)), cap, C.byref(n)))
+        return n.value
 
     def compact_segments(self, cloth=0):
         """Device-side live-stick compaction only (asynchronous)."""
