@@ -1043,6 +1043,107 @@ int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const doub
     return CLOTHGPU_OK;
 }
 
+namespace {
+struct StateFileHeader {
+    char magic[8];
+    uint32_t header_bytes, version;
+    int32_t nx, ny, row0, rows;
+    int32_t ensemble, spacing, pos_x, pos_y;
+    uint64_t frames, reserved;
+};
+static_assert(sizeof(StateFileHeader) == 64, "state file header is 64 bytes");
+constexpr char kStateMagic[8] = {'C', 'L', 'S', 'T', 'A', 'T', 'E', '1'};
+
+uint64_t fnv1a64(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+constexpr uint64_t kFnvBasis = 0xcbf29ce484222325ull;
+}  // namespace
+
+int clothgpu_save_state(clothgpu* c, const char* path) {
+    if (int rc = check_handle(c)) return rc;
+    if (!path) return fail(CLOTHGPU_ERR_INVALID, "null path");
+    const Geom& g = c->g;
+    const size_t n = (size_t)g.nx * g.own_rows, nfl = (n + 7) / 8 * 8;
+    StateFileHeader h{};
+    memcpy(h.magic, kStateMagic, 8);
+    h.header_bytes = 64, h.version = 1;
+    h.nx = g.nx, h.ny = c->ny, h.row0 = g.own_row0, h.rows = g.own_rows;
+    h.ensemble = g.ensemble, h.spacing = c->desc.spacing, h.pos_x = c->desc.pos_x, h.pos_y = c->desc.pos_y;
+    h.frames = c->frames;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CLOTHGPU_ERR_INVALID, "cannot open %s for writing", path);
+    uint64_t sum = fnv1a64(kFnvBasis, &h, sizeof h);
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    std::vector<double> plane[4];
+    for (auto& p : plane) p.resize(n);
+    std::vector<uint8_t> fl(nfl, 0);
+    int rc = CLOTHGPU_OK;
+    for (int e = 0; e < g.ensemble && ok && rc == CLOTHGPU_OK; ++e) {
+        rc = clothgpu_read_state(c, e, plane[0].data(), plane[1].data(), plane[2].data(), plane[3].data(), fl.data());
+        if (rc != CLOTHGPU_OK) break;
+        for (auto& p : plane) {
+            sum = fnv1a64(sum, p.data(), n * sizeof(double));
+            ok = ok && (n == 0 || fwrite(p.data(), sizeof(double), n, f) == n);
+        }
+        sum = fnv1a64(sum, fl.data(), nfl);
+        ok = ok && (nfl == 0 || fwrite(fl.data(), 1, nfl, f) == nfl);
+    }
+    ok = ok && fwrite(&sum, sizeof sum, 1, f) == 1;
+    ok = (fclose(f) == 0) && ok;
+    if (rc != CLOTHGPU_OK) return rc;
+    if (!ok) return fail(CLOTHGPU_ERR_INVALID, "short write to %s", path);
+    return CLOTHGPU_OK;
+}
+
+int clothgpu_load_state(clothgpu* c, const char* path) {
+    if (int rc = check_handle(c)) return rc;
+    if (!path) return fail(CLOTHGPU_ERR_INVALID, "null path");
+    const Geom& g = c->g;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(CLOTHGPU_ERR_INVALID, "cannot open %s", path);
+    StateFileHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kStateMagic, 8) != 0 || h.header_bytes != 64 || h.version != 1) {
+        fclose(f);
+        return fail(CLOTHGPU_ERR_INVALID, "%s is not a clothgpu state file (CLSTATE1, version 1)", path);
+    }
+    if (h.nx != g.nx || h.ny != c->ny || h.row0 != g.own_row0 || h.rows != g.own_rows || h.ensemble != g.ensemble) {
+        fclose(f);
+        return fail(CLOTHGPU_ERR_INVALID, "%s holds %d cloth(s) of %dx%d, rows [%d,%d); the handle holds %d of %dx%d, rows [%d,%d)", path,
+                    h.ensemble, h.nx, h.ny, h.row0, h.row0 + h.rows, g.ensemble, g.nx, c->ny, g.own_row0, g.own_row0 + g.own_rows);
+    }
+    const size_t n = (size_t)g.nx * g.own_rows, nfl = (n + 7) / 8 * 8;
+    // first pass: read everything and verify the checksum, so a damaged file leaves the handle untouched
+    std::vector<std::vector<double>> planes((size_t)g.ensemble * 4);
+    std::vector<std::vector<uint8_t>> flags((size_t)g.ensemble);
+    uint64_t sum = fnv1a64(kFnvBasis, &h, sizeof h), stored = 0;
+    bool ok = true;
+    for (int e = 0; e < g.ensemble && ok; ++e) {
+        for (int k = 0; k < 4 && ok; ++k) {
+            auto& p = planes[(size_t)e * 4 + k];
+            p.resize(n);
+            ok = n == 0 || fread(p.data(), sizeof(double), n, f) == n;
+            sum = fnv1a64(sum, p.data(), n * sizeof(double));
+        }
+        flags[e].resize(nfl);
+        ok = ok && (nfl == 0 || fread(flags[e].data(), 1, nfl, f) == nfl);
+        sum = fnv1a64(sum, flags[e].data(), nfl);
+    }
+    ok = ok && fread(&stored, sizeof stored, 1, f) == 1;
+    fclose(f);
+    if (!ok) return fail(CLOTHGPU_ERR_INVALID, "%s is truncated", path);
+    if (stored != sum) return fail(CLOTHGPU_ERR_INVALID, "%s: checksum mismatch (file damaged)", path);
+    for (int e = 0; e < g.ensemble; ++e) {
+        const auto* p = &planes[(size_t)e * 4];
+        if (int rc = clothgpu_write_state(c, e, p[0].data(), p[1].data(), p[2].data(), p[3].data(), flags[e].data())) return rc;
+    }
+    c->frames = h.frames;
+    c->census_valid = false;
+    return CLOTHGPU_OK;
+}
+
 int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* active, uint32_t* highlighted,
                         uint32_t* alive_h, uint32_t* alive_v) {
     if (int rc = check_handle(c)) return rc;

@@ -1,3 +1,5 @@
+//go:build cgo && !refharness
+
 // Package physics — cgo binding of libclothgpu.so behind the reference's exported surface.
 //
 // SOURCE ONLY: this image has no Go toolchain, so this file is not compiled or tested here; the
@@ -36,6 +38,7 @@ import (
 	"gioui.org/op/paint"
 
 	"github.com/esimov/cloth-physics/gui"
+	"github.com/esimov/cloth-physics/utils"
 )
 
 const strokeWidth = 0.6
@@ -49,6 +52,12 @@ type Cloth struct {
 	spacing int
 	tint    color.NRGBA
 	gpu     *C.clothgpu
+	// grid the handle was created for and its stick count at Init (constant per handle: read once, not per frame)
+	nx, ny    int
+	capSticks int
+	posX      int
+	posY      int
+	frames    uint64
 	// host staging for the render export, reused across frames
 	quads []float32
 	hl    []uint8
@@ -75,6 +84,12 @@ func (c *Cloth) Init(posX, posY int, hud *gui.Hud) {
 	if rc := C.clothgpu_create(&d, &c.gpu); rc != C.CLOTHGPU_OK {
 		panic(fmt.Sprintf("clothgpu_create: %s", C.GoString(C.clothgpu_last_error())))
 	}
+	var info C.clothgpu_info
+	C.clothgpu_get_info(c.gpu, &info)
+	c.nx, c.ny, c.capSticks = int(info.nx), int(info.ny), int(info.sticks)
+	c.posX, c.posY, c.frames = posX, posY, 0
+	// Close clears the finalizer again, so Reset may re-Init the same object after a resize (main.go:190-193) without
+	// "runtime.SetFinalizer: finalizer already set".
 	runtime.SetFinalizer(c, (*Cloth).Close)
 }
 
@@ -85,28 +100,51 @@ func (c *Cloth) Reset(startX, startY int, hud *gui.Hud) {
 		return
 	}
 	// Width/Height may have been changed by main.go:190-191; a different grid needs a new handle.
-	var info C.clothgpu_info
-	C.clothgpu_get_info(c.gpu, &info)
-	if int(info.nx) != c.Width/c.spacing+1 || int(info.ny) != c.Height/c.spacing+1 {
+	if c.nx != c.Width/c.spacing+1 || c.ny != c.Height/c.spacing+1 {
 		c.Close()
 		c.Init(startX, startY, hud)
 		return
 	}
 	c.check(C.clothgpu_reset(c.gpu, C.int32_t(startX), C.int32_t(startY)))
+	c.posX, c.posY, c.frames = startX, startY, 0
 }
 
 // Close releases the device memory (the reference relies on the GC; there is no counterpart).
 func (c *Cloth) Close() {
 	if c.gpu != nil {
+		runtime.SetFinalizer(c, nil)
 		C.clothgpu_destroy(c.gpu)
 		c.gpu = nil
 	}
+}
+
+// Dump writes a CLSTATE1 snapshot (include/clothgpu.h) — same signature as the Dump that dump_harness.go adds to the
+// reference's package, so host/go/harness drives either implementation.
+func (c *Cloth) Dump(path string, posX, posY int, frames uint64) error {
+	cs := C.CString(path)
+	defer C.free(unsafe.Pointer(cs))
+	if rc := C.clothgpu_save_state(c.gpu, cs); rc != C.CLOTHGPU_OK {
+		return fmt.Errorf("clothgpu_save_state: %s", C.GoString(C.clothgpu_last_error()))
+	}
+	return nil
+}
+
+// SliceLen is len(cloth.constraints) of the reference: the sticks not torn yet.
+func (c *Cloth) SliceLen() int {
+	var k C.clothgpu_counters
+	c.check(C.clothgpu_get_counters(c.gpu, &k))
+	return int(k.alive_sticks)
 }
 
 // Update mirrors physics/cloth.go:85-138: the physics half runs on the GPU, the render half walks the
 // compacted live-stick list the device exports (same order and same float32 endpoints as the two
 // loops of cloth.go:108-114 and 126-134).
 func (c *Cloth) Update(gtx layout.Context, mouse *Mouse, hud *gui.Hud, dt float64) {
+	// cloth.go:86-90: the highlight path's colour is the cloth's red lightened by the drag force
+	dragForce := float32(mouse.GetForce() * 0.1)
+	clothColor := color.NRGBA{R: 0x55, A: 0xff}
+	col := utils.LinearFromSRGB(clothColor).HSLA().Lighten(dragForce).RGBA().SRGB()
+
 	var f C.clothgpu_frame
 	C.clothgpu_frame_default(&f)
 	// particle.go:78-83: the five sliders are read as float32 and widened at the point of use
@@ -123,19 +161,19 @@ func (c *Cloth) Update(gtx layout.Context, mouse *Mouse, hud *gui.Hud, dt float6
 	f.dt = C.double(dt)
 	f.iterations = 1 // the reference relaxes once per frame (cloth.go:96-100)
 	c.check(C.clothgpu_step(c.gpu, &f))
+	c.frames++
 
 	// render half, cloth.go:102-138: the device applies addSegment / normal (cloth.go:150-168) to every live stick and
 	// hands back the four corners of its outline quad, in the order the two loops of cloth.go:108-114 / 126-134 walk
-	var info C.clothgpu_info
-	C.clothgpu_get_info(c.gpu, &info)
-	capSticks := int(info.sticks)
-	if cap(c.quads) < 8*capSticks {
-		c.quads = make([]float32, 8*capSticks)
-		c.hl = make([]uint8, capSticks)
-	}
 	var n C.size_t
-	c.check(C.clothgpu_read_quads_f32(c.gpu, 0, C.float(strokeWidth), (*C.float)(unsafe.Pointer(&c.quads[0])),
-		(*C.uint8_t)(unsafe.Pointer(&c.hl[0])), C.size_t(capSticks), &n))
+	if c.capSticks > 0 { // (a 1 x 1 "cloth" has no sticks: nothing to read back, and &c.quads[0] would panic)
+		if len(c.quads) < 8*c.capSticks {
+			c.quads = make([]float32, 8*c.capSticks)
+			c.hl = make([]uint8, c.capSticks)
+		}
+		c.check(C.clothgpu_read_quads_f32(c.gpu, 0, C.float(strokeWidth), (*C.float)(unsafe.Pointer(&c.quads[0])),
+			(*C.uint8_t)(unsafe.Pointer(&c.hl[0])), C.size_t(c.capSticks), &n))
+	}
 
 	var path clip.Path
 	path.Begin(gtx.Ops)
@@ -149,7 +187,7 @@ func (c *Cloth) Update(gtx layout.Context, mouse *Mouse, hud *gui.Hud, dt float6
 			outline(&path, c.quads[8*i:8*i+8])
 		}
 	}
-	paint.FillShape(gtx.Ops, color.NRGBA{R: c.tint.R, A: c.tint.A}, clip.Outline{Path: path.End()}.Op())
+	paint.FillShape(gtx.Ops, color.NRGBA{R: col.R, A: col.A}, clip.Outline{Path: path.End()}.Op()) // cloth.go:136
 }
 
 // outline adds one stick's quad {a+n, b+n, b-n, a-n} to the path, as addSegment does (cloth.go:150-157).

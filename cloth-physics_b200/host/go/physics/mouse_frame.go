@@ -1,3 +1,5 @@
+//go:build cgo && !refharness
+
 // mouse_frame.go — the one addition next to the reference's unchanged physics/mouse.go: copy the
 // Mouse (physics/mouse.go:9-19) into the fields of a clothgpu_frame, i.e. everything
 // particle.update / constraint.Update read from it (particle.go:96-149, constraint.go:35).

@@ -26,7 +26,7 @@ EXPORTS = [
     "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_read_quads_f32", "clothgpu_compact_segments",
     "clothgpu_get_counters",
     "clothgpu_halo_region", "clothgpu_strip_export", "clothgpu_strip_attach", "clothgpu_strip_push", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
-    "clothgpu_last_schedule", "clothgpu_selftest_stickmath",
+    "clothgpu_last_schedule", "clothgpu_selftest_stickmath", "clothgpu_save_state", "clothgpu_load_state",
     "clothgpu_last_error", "clothgpu_version",
 ]
 
@@ -63,6 +63,9 @@ def lib():
         L.clothgpu_set_schedule.argtypes = [vp, C.c_int32]
         L.clothgpu_read_state.argtypes = [vp, C.c_int32, dp, dp, dp, dp, u8p]
         L.clothgpu_write_state.argtypes = [vp, C.c_int32, dp, dp, dp, dp, u8p]
+        if hasattr(L, "clothgpu_save_state"):
+            L.clothgpu_save_state.argtypes = [vp, C.c_char_p]
+            L.clothgpu_load_state.argtypes = [vp, C.c_char_p]
         L.clothgpu_read_masks.argtypes = [vp, C.c_int32, u32p, u32p, u32p, u32p, u32p]
         L.clothgpu_read_segments_f32.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), u8p, u32p,
                                                  C.c_size_t, C.POINTER(C.c_size_t)]
@@ -183,6 +186,13 @@ class Cloth:
             assert a is None or a.size == self.nx * self.rows
         _check(self._L.clothgpu_write_state(self._h, cloth, *[_p(a, C.c_double) for a in arrs],
                                             _p(fl, C.c_uint8)))
+
+    def save_state(self, path):
+        """Snapshot of the whole handle on disk (CLSTATE1, include/clothgpu.h)."""
+        _check(self._L.clothgpu_save_state(self._h, os.fsencode(path)))
+
+    def load_state(self, path):
+        _check(self._L.clothgpu_load_state(self._h, os.fsencode(path)))
 
     def read_masks(self, cloth=0):
         w = (self.nx * self.rows + 31) // 32

@@ -216,6 +216,24 @@ CLOTHGPU_API int clothgpu_read_state(clothgpu* c, int32_t cloth, double* x, doub
 CLOTHGPU_API int clothgpu_write_state(clothgpu* c, int32_t cloth, const double* x, const double* y,
                          const double* px, const double* py, const uint8_t* flags);
 
+/* On-disk snapshot of everything the handle owns (no reference counterpart: the reference's only state transition
+ * besides Update is Reset, physics/cloth.go:142-148).  One little-endian file:
+ *     char     magic[8] = "CLSTATE1"
+ *     uint32   header_bytes = 64, version = 1
+ *     int32    nx, ny, row0, rows        particles per row / rows of the whole cloth; the owned rows stored here
+ *     int32    ensemble, spacing, pos_x, pos_y
+ *     uint64   frames                    frames stepped since create / reset
+ *     uint64   reserved = 0
+ *     per cloth: double x[rows*nx], y[], px[], py[]; uint8 flags[rows*nx] (CLOTHGPU_FLAG_* bits), zero-padded to 8 bytes
+ *     uint64   FNV-1a 64 of every byte before it
+ * i.e. particle{x,y,px,py,pinX,isActive,highlighted} (physics/particle.go:16-27) plus stick membership, in the row-major
+ * order of Cloth.particles.  F32 handles store their values widened to double.  clothgpu_save_state synchronises;
+ * clothgpu_load_state needs a handle of the same geometry (nx, ny, owned rows, ensemble), validates the checksum and the
+ * values as clothgpu_write_state does, and restores the frame count; attached strips call clothgpu_strip_push after it.
+ * host/go/physics/dump_harness.go writes the same file from the unmodified reference. */
+CLOTHGPU_API int clothgpu_save_state(clothgpu* c, const char* path);
+CLOTHGPU_API int clothgpu_load_state(clothgpu* c, const char* path);
+
 /* Bit-planes of the flag byte, 1 bit per particle, LSB first, ceil(particles/32) words each; any
  * pointer may be NULL. */
 CLOTHGPU_API int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* active,

@@ -6,7 +6,11 @@ PARITY UNPINNED: the reference cannot be built here (no Go toolchain), so these 
 They freeze its behaviour (compiler / flag / refactoring regressions) and give the GPU tests an oracle-independent
 target at run time.  With a Go toolchain, host/go/harness regenerates them from the real reference.
 
-    python tests/golden/make_golden.py          # rewrites c0_golden.json
+    python tests/golden/make_golden.py                # rewrites c0_golden.json
+    python tests/golden/make_golden.py --dump-trace   # rewrites c0_trace.jsonl: the scripted trace as JSON lines
+                                                      # (clothgpu/trace.py), the input of host/go/harness/main.go
+    python tests/golden/make_golden.py --dump-states DIR   # CLSTATE1 snapshots of the oracle (all three modes) at the
+                                                      # checkpoints, to diff against the Go harness's dumps
 """
 import hashlib
 import json
@@ -57,7 +61,34 @@ def run(pyoracle, _abi, c0_trace, mode, K):
     return recs
 
 
+def dump_trace(path):
+    from clothgpu.trace import RecordingMouse, TraceRecorder
+    from traces import c0_trace
+    rec = TraceRecorder(RecordingMouse())
+    c0_trace(1000, recorder=rec)
+    rec.save(path)
+    print("wrote", path, len(rec.records), "frames")
+
+
+def dump_states(out_dir):
+    import pyoracle
+    from clothgpu import _abi, statefile
+    from traces import c0_trace
+    os.makedirs(out_dir, exist_ok=True)
+    for mode, code in MODES.items():
+        o = pyoracle.OracleCloth(_abi.default_desc(), code)
+        for t, f in enumerate(c0_trace(1000)):
+            o.step(f)
+            if t in CHECKPOINTS:
+                statefile.write(os.path.join(out_dir, f"c0_{mode}_{t:04d}.clstate"), 171, 36, [o.read_state()], frames=t + 1)
+    print("wrote", out_dir)
+
+
 def main():
+    if "--dump-trace" in sys.argv:
+        return dump_trace(os.path.join(HERE, "c0_trace.jsonl"))
+    if "--dump-states" in sys.argv:
+        return dump_states(sys.argv[sys.argv.index("--dump-states") + 1])
     import pyoracle
     from clothgpu import _abi
     from traces import c0_trace

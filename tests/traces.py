@@ -6,12 +6,12 @@ from clothgpu.mouse import EventAdapter
 P, S = EventAdapter.PRIMARY, EventAdapter.SECONDARY
 
 
-def c0_trace(n_frames=1000, iterations=1, scale=1.0, win=(1280, 820), pin_click=(128 + 6 * 40, 164 + 6 * 10)):
+def c0_trace(n_frames=1000, iterations=1, scale=1.0, win=(1280, 820), pin_click=(128 + 6 * 40, 164 + 6 * 10), recorder=None):
     """frame 2 ctrl-click on particle (40,10) while the cloth is still (almost) at its rest grid, so the click really
     pins it; frames 3-99 idle; 100-399 slow left-drag sweep with the force ramp; 400-449 released;
     450-549 right-button hold moving along a line (hole punch); 550-599 scroll the focus area to 120;
     600-799 fast zig-zag left-drag (tears); 800 ctrl-click on a particle; then idle."""
-    ad = EventAdapter()
+    ad = EventAdapter(recorder.mouse if recorder is not None else None)
     frames = []
     press_frame = None
     for t in range(n_frames):
@@ -60,5 +60,7 @@ def c0_trace(n_frames=1000, iterations=1, scale=1.0, win=(1280, 820), pin_click=
         f = _abi.default_frame(iterations)
         f.win_w, f.win_h = win
         ad.mouse.fill(f)
+        if recorder is not None:   # clothgpu.trace.TraceRecorder: the frame as a JSON-lines record (replayable by the Go harness)
+            recorder.end_frame(win=win, dt=f.dt, iterations=iterations)
         frames.append(f)
     return frames
