@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kStreamThreads)
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     const long long n = (long long)g.held_rows * g.pitch;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    prepare_next_frame_counters(ctr);
     ParticleEvents events;
     if (i < n && (int)(i % g.pitch) < g.nx) {
         const long long at = (long long)e * g.cloth_stride + i;

@@ -90,10 +90,15 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     using V2 = typename Vec2<T>::type;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    prepare_next_frame_counters(ctr);
     const long long task = (long long)blockIdx.x * (kS1Threads / 32) + (threadIdx.x >> 5);
     if (task >= pl.tasks) return;  // whole warp
     const int w = (int)(task % pl.windows);
-    const int chunk = (int)((task / pl.windows) % pl.chunks);
+    // Row chunks are issued edges first (top, bottom, then the interior from the top down): the chunks that store into
+    // the neighbouring strips' ghost rows — and publish the epoch the neighbours' next frame waits for — then finish in
+    // the first wave instead of the last.
+    const int ci = (int)((task / pl.windows) % pl.chunks);
+    const int chunk = ci == 0 ? 0 : ci == 1 ? pl.chunks - 1 : ci - 1;
     const int e = (int)(task / ((long long)pl.windows * pl.chunks));
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     const bool dragging = DRAG && (u.buttons & CLOTHGPU_MOUSE_DRAGGING) != 0;

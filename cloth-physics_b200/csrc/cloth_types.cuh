@@ -77,15 +77,31 @@ struct FrameU {
 
 // Device-side counters accumulated by the frame kernels themselves (warp-reduced, one atomic per warp that saw an
 // event), so that clothgpu_get_counters is one small copy instead of a census launch.
-struct DevCounters {
+// A handle owns TWO of these, adjacent and 128-byte aligned; frame f accumulates into slot f & 1 (the host sums the two
+// slots for the cumulative fields and reads the *_last fields of the slot of the last frame).  The first kernel of a frame
+// zeroes the *_last fields of the OTHER slot — nobody touches that one until the next frame — so no memset node sits
+// between two frame kernels on the stream.
+struct alignas(64) DevCounters {
     unsigned long long relaxations;   // stick visits
     unsigned long long torn_total;
-    unsigned long long torn_last;     // the three *_last slots are zeroed (stream ordered) before each frame
-    unsigned long long live_last;     // sticks the next frame's loop would relax (cloth.go:97), after the last launch
+    unsigned long long torn_last;     // sticks torn by the frame
+    unsigned long long live_last;     // sticks the next frame's loop would relax (cloth.go:97), after the frame's last launch
     unsigned long long hl_last;       // particles highlighted by the frame (particle.go:140-142)
     unsigned long long pinned_new;    // particles pinned by ctrl-click (particle.go:128-130) since the last census
     unsigned long long inactive_new;  // particles deactivated by the right button (particle.go:145-149) since then
+    unsigned long long pad_;
 };
+static_assert(sizeof(DevCounters) == 64, "two slots are told apart by address bit 6");
+
+// Called by every thread of the first kernel of a frame: one thread clears the per-frame fields of the other slot.
+__device__ __forceinline__ void prepare_next_frame_counters(DevCounters* ctr) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        DevCounters* other = reinterpret_cast<DevCounters*>(reinterpret_cast<unsigned long long>(ctr) ^ 64ull);
+        other->torn_last = 0ull;
+        other->live_last = 0ull;
+        other->hl_last = 0ull;
+    }
+}
 
 // What the particle loop changed on the particles a thread owns (events are rare: they need the mouse nearby).
 struct ParticleEvents {

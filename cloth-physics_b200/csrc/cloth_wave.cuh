@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(stage + kWaveDepth * 2 * 4 * HW);  // [kWaveDepth]
 
     const int tid = threadIdx.x;
+    prepare_next_frame_counters(ctr);
     unsigned int acc_live = 0, acc_torn = 0, acc_torn_post = 0, acc_extra = 0;
     ParticleEvents events;
     unsigned int stage_parity = 0;  // entry warps: bit d = phase parity of staging slot d's mbarrier (runs on across chunks)

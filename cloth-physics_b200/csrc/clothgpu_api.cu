@@ -68,7 +68,9 @@ struct clothgpu {
     void* PY[2] = {nullptr, nullptr};
     uint8_t* FL[2] = {nullptr, nullptr};
     int cur_pos = 0, cur_prev = 0;
-    DevCounters* ctr = nullptr;           // accumulated by the frame kernels (cloth_types.cuh)
+    DevCounters* ctr_base = nullptr;      // two slots, accumulated by the frame kernels (cloth_types.cuh): frame f uses slot f & 1
+    DevCounters* ctr = nullptr;           // the slot of the frame being issued / issued last
+    int ctr_slot = 0;                     // slot the NEXT frame will use
     unsigned long long* census = nullptr; // 5 values, written by count_kernel
     // Pinned staging for clothgpu_get_counters: [0] a DevCounters, then the 5 census values.
     unsigned char* ctr_host = nullptr;
@@ -585,9 +587,9 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         CU_TRY(cudaEventRecord(c->frames_copied, c->stream));
         dev_frames = (const FrameU<T>*)c->frames_dev;
     }
-    // torn_last, live_last, hl_last: the frame kernels accumulate this frame's values (cloth_types.cuh, DevCounters)
-    static_assert(offsetof(DevCounters, hl_last) == offsetof(DevCounters, torn_last) + 2 * sizeof(unsigned long long), "layout");
-    CU_TRY(cudaMemsetAsync(&c->ctr->torn_last, 0, 3 * sizeof(unsigned long long), c->stream));
+    // torn_last, live_last, hl_last of this frame's counter slot were zeroed by the previous frame's first kernel
+    // (cloth_types.cuh, prepare_next_frame_counters): no memset node between two frame kernels
+    c->ctr = c->ctr_base + c->ctr_slot;
     int sched = c->schedule;
     if (sched == CLOTHGPU_SCHED_AUTO) {
         // One sweep: the row-streaming kernel, unless the cloth is too small to feed enough independent warps.
@@ -632,6 +634,7 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     if (rc == CLOTHGPU_OK) {
         c->frames++;
         c->last_sched = sched;
+        c->ctr_slot ^= 1;
     }
     return rc;
 }
@@ -654,7 +657,9 @@ int init_state(clothgpu* c, int pos_x, int pos_y) {
                                                                 pos_y, c->desc.pin_rule);
     CU_TRY(cudaGetLastError());
     c->launches++;
-    CU_TRY(cudaMemsetAsync(c->ctr, 0, sizeof(DevCounters), c->stream));
+    CU_TRY(cudaMemsetAsync(c->ctr_base, 0, 2 * sizeof(DevCounters), c->stream));
+    c->ctr = c->ctr_base;
+    c->ctr_slot = 0;
     c->frames = 0;
     c->census_valid = false;
     return strip_end_op(c);
@@ -666,7 +671,7 @@ void free_all(clothgpu* c) {
     for (auto& l : c->link)
         if (l.on && l.ipc) cudaIpcCloseMemHandle(l.base);
     cudaFree(c->slab);
-    cudaFree(c->ctr);
+    cudaFree(c->ctr_base);
     cudaFree(c->census);
     cudaFreeHost(c->ctr_host);
     cudaFree(c->frames_dev);
@@ -848,11 +853,12 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
             c->ticket = (unsigned long long*)(b + c->off_slots + 64);
         }
     }
-    alloc((void**)&c->ctr, sizeof(DevCounters));
+    alloc((void**)&c->ctr_base, 2 * sizeof(DevCounters));
+    c->ctr = c->ctr_base;
     alloc((void**)&c->census, 5 * sizeof(unsigned long long));
     alloc((void**)&c->seg_total, sizeof(unsigned long long));
     if (rc == CLOTHGPU_OK) {
-        cudaError_t ee = cudaMallocHost((void**)&c->ctr_host, sizeof(DevCounters) + 5 * sizeof(unsigned long long));
+        cudaError_t ee = cudaMallocHost((void**)&c->ctr_host, 2 * sizeof(DevCounters) + 5 * sizeof(unsigned long long));
         if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(ee));
     }
     const size_t fbytes = sizeof(FrameU<double>) * (size_t)ensemble;
@@ -1286,8 +1292,8 @@ int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
     if (int rc = check_handle(c)) return rc;
     if (!out) return fail(CLOTHGPU_ERR_INVALID, "null out");
     const Geom& g = c->g;
-    DevCounters* hc = (DevCounters*)c->ctr_host;
-    unsigned long long* h5 = (unsigned long long*)(c->ctr_host + sizeof(DevCounters));
+    DevCounters* h2 = (DevCounters*)c->ctr_host;  // both slots
+    unsigned long long* h5 = (unsigned long long*)(c->ctr_host + 2 * sizeof(DevCounters));
     const bool census = !c->census_valid;
     if (census) {
         // the flag bytes changed behind the frame kernels' back (create, reset, write_state): count them once
@@ -1303,10 +1309,17 @@ int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
         CU_TRY(cudaMemcpyAsync(h5, c->census, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         // the census includes everything the queued frames did: their deltas start again from zero
         static_assert(offsetof(DevCounters, inactive_new) == offsetof(DevCounters, pinned_new) + sizeof(unsigned long long), "layout");
-        CU_TRY(cudaMemsetAsync(&c->ctr->pinned_new, 0, 2 * sizeof(unsigned long long), c->stream));
+        for (int k = 0; k < 2; ++k) CU_TRY(cudaMemsetAsync(&c->ctr_base[k].pinned_new, 0, 2 * sizeof(unsigned long long), c->stream));
     }
-    CU_TRY(cudaMemcpyAsync(hc, c->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(h2, c->ctr_base, 2 * sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    // cumulative fields: the sum of the two slots; per-frame fields: the slot of the last frame
+    DevCounters sum = h2[c->ctr - c->ctr_base];
+    {
+        const DevCounters& o = h2[1 - (c->ctr - c->ctr_base)];
+        sum.relaxations += o.relaxations, sum.torn_total += o.torn_total, sum.pinned_new += o.pinned_new, sum.inactive_new += o.inactive_new;
+    }
+    const DevCounters* hc = &sum;
     if (census) {
         c->base.live = h5[0];
         c->base.alive = h5[1];
