@@ -322,8 +322,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             uint32_t f = 0;
             if (ra_.ok) {
                 f = *reinterpret_cast<const unsigned short*>(in.fl + ra_.at);
-                if (pk_cc + 1 >= col_end) f &= 0xffu;  // column nx (row padding) does not exist
+                // (the value is consumed a step later: without PACK nothing touches it here, so the warp does not wait for
+                //  the load; the non-existent column nx of the row padding is masked at the point of use)
                 if (PACK) {
+                    if (pk_cc + 1 >= col_end) f &= 0xffu;
                     // Next to / below a cloth's edge lies ANOTHER cloth here: the edge particles must head no stick.  Their
                     // alive bits (meaningless, but part of the state the caller may have written) are parked in the spare
                     // bits 5 / 6 of the flag byte — no pass looks at those — and restored when the row is written back.
@@ -389,7 +391,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 } else {
                     cp_async_wait<kWaveDepth - 1>();
                 }
-                const uint32_t fcur[2] = {fnext[0], fnext[1]};
+                const uint32_t fkeep = (PACK || pk_cc + 1 < col_end) ? 0xffffu : 0xffu;
+                const uint32_t fcur[2] = {fnext[0] & fkeep, fnext[1] & fkeep};
                 fnext[0] = load_flags(q + 1, 0), fnext[1] = load_flags(q + 1, 1);
                 V2 p0[2], p1[2];
                 uint32_t f0[2], f1[2];
