@@ -3,7 +3,7 @@
 //   init_grid_kernel        <- (*Cloth).Init                          physics/cloth.go:42-81
 //   verlet_kernel           <- loop over particles                    physics/cloth.go:92-94
 //   relax_pass_kernel<C>    <- loop over sticks, one colour at a time physics/cloth.go:96-100
-//   count_kernel / pack_masks_kernel / segment kernels: read-back helpers
+//   count_kernel / pack_masks_kernel / segment_export_kernel: read-back helpers
 //
 // The streaming schedule moves 64 B per stick relaxation through L2/HBM (2 endpoints x 16 B, read and
 // write) and is the correctness cross-check and the "unfused" companion figure of DESIGN.md; the
@@ -239,117 +239,67 @@ __global__ void __launch_bounds__(kStreamThreads)
 // Sticks are listed in the order Cloth.Init created them (physics/cloth.go:61-70): by TAIL particle in
 // row-major order, the vertical stick (from the particle above) before the horizontal one (from the
 // particle to the left).  A stick is listed when it is still in the slice and both endpoints are
-// active.  Three launches: per-block counts, a one-block exclusive scan, ballot-ranked scatter.
-template <typename T>
-__device__ __forceinline__ int tail_sticks(const Planes<T>& P, const Geom& g, long long base, int ly,
-                                           int cx, bool& v_live, bool& h_live) {
-    // ly counts owned rows; the row above the first owned row is a ghost row (strip) or absent
-    v_live = h_live = false;
-    const long long at = base + (long long)(g.own_row0 - g.held_row0 + ly) * g.pitch + cx;
-    const uint32_t f = P.fl[at];
-    if (!(f & CLOTHGPU_FLAG_ACTIVE)) return 0;
-    if (g.own_row0 + ly > g.held_row0) {
-        const uint32_t fu = P.fl[at - g.pitch];
-        v_live = (fu & CLOTHGPU_FLAG_ALIVE_V) && (fu & CLOTHGPU_FLAG_ACTIVE);
-    }
-    if (cx > 0) {
-        const uint32_t fw = P.fl[at - 1];
-        h_live = (fw & CLOTHGPU_FLAG_ALIVE_H) && (fw & CLOTHGPU_FLAG_ACTIVE);
-    }
-    return (int)v_live + (int)h_live;
-}
-
-// Sticks per block of kSegBlock consecutive particles of the owned rows in PADDED row-major order (padding columns
-// hold zero flags and add nothing, so the order of the listed sticks is the unpadded one).  16 flag bytes per thread,
-// byte-parallel tests: tail t lists its vertical stick when t and the particle above are active and that particle's
-// ALIVE_V bit is set, its horizontal stick likewise with the particle to the left.
+// active.  ONE launch: every block of kSegBlock consecutive particles counts its sticks from the flag bytes, obtains
+// its place in the list by a decoupled look-back over the blocks before it, and scatters.
 constexpr int kSegPerThread = 16;
 constexpr int kSegBlock = kStreamThreads * kSegPerThread;
 
-template <typename T>
-__global__ void __launch_bounds__(kStreamThreads)
-    segment_count_kernel(Planes<T> P, Geom g, int cloth, unsigned int* __restrict__ block_counts) {
-    const long long chunks = (long long)g.own_rows * g.pitch / 16;
-    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const uint8_t* base = P.fl + (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
-    unsigned long long n = 0;
-    if (c < chunks) {
-        constexpr uint32_t k1 = 0x01010101u;
-        const long long off = c * 16;
-        const int ly = (int)(off / g.pitch), cx = (int)(off - (long long)ly * g.pitch);
-        const uint4 w4 = *reinterpret_cast<const uint4*>(base + off);
-        uint4 u4 = make_uint4(0, 0, 0, 0);  // the row above: a ghost row of a strip, or absent at the cloth's top
-        if (g.own_row0 + ly > g.held_row0) u4 = *reinterpret_cast<const uint4*>(base + off - g.pitch);
-        const uint32_t left = cx > 0 ? base[off - 1] : 0u;
-        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
-        uint32_t carry = left;  // flag byte of the particle left of word q
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t f = w[q], act = (f >> 1) & k1;
-            const uint32_t fl_left = (f << 8) | (carry & 0xffu);  // each byte: the flags of its left neighbour
-            const uint32_t v = act & (up[q] >> 4) & (up[q] >> 1) & k1;
-            const uint32_t h = act & (fl_left >> 3) & (fl_left >> 1) & k1;
-            n += __popc(v) + __popc(h);
-            carry = f >> 24;
-        }
-    }
-    const unsigned long long s = block_sum_ull(n);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned int)s;  // 256 threads x 16 particles = one scatter block
+// Decoupled look-back status of one block: epoch (29 bits) | flag (2 bits) | value (33 bits).  The epoch is the launch
+// number, so the array is never cleared: a word of an earlier launch simply reads as "nothing yet".
+constexpr unsigned long long kSegFlagAggregate = 1ull, kSegFlagPrefix = 2ull;
+__device__ __forceinline__ unsigned long long seg_status(unsigned int epoch, unsigned long long flag, unsigned long long value) {
+    return ((unsigned long long)(epoch & 0x1fffffffu) << 35) | (flag << 33) | (value & 0x1ffffffffull);
 }
 
-// exclusive scan of block_counts in place (single block); total -> *total_out
-__global__ void __launch_bounds__(1024)
-    segment_scan_kernel(unsigned int* __restrict__ block_counts, int n,
-                        unsigned long long* __restrict__ total_out) {
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const unsigned long long v = i < n ? block_counts[i] : 0;
-        unsigned long long inc = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) warp_tot[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            unsigned long long t = warp_tot[lane];
-            unsigned long long ti = t;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long q = __shfl_up_sync(0xffffffffu, ti, o);
-                if (lane >= o) ti += q;
-            }
-            warp_tot[lane] = ti - t;  // exclusive across warps
-        }
-        __syncthreads();
-        const unsigned long long excl = carry + warp_tot[w] + inc - v;
-        if (i < n) block_counts[i] = (unsigned int)excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
+// addSegment / normal of the reference's render loops (physics/cloth.go:150-168) for one stick a -> b: the four float32
+// corners {a+n, b+n, b-n, a-n} of its outline quad, n = the stick's normal scaled to the line width.  math.Hypot is
+// max * sqrt(1 + (min/max)^2) in binary64 (hypot_amd64.s); everything else is float32 arithmetic, one rounding per
+// operation (-fmad=false, IEEE division).
+__device__ __forceinline__ void segment_quad(const float4 s, float line_width, float4& q0, float4& q1) {
+    const float dx = s.z - s.x, dy = s.w - s.y;  // dir := b.Sub(a)
+    const float rx = +dy, ry = -dx;              // dir.X, dir.Y = +dir.Y, -dir.X
+    double p = fabs((double)rx), q = fabs((double)ry);
+    if (p < q) {
+        const double t = p;
+        p = q, q = t;
     }
-    if (threadIdx.x == 0) *total_out = carry;
+    double d = 0.0;
+    if (p != 0.0) {
+        q = q / p;
+        d = p * sqrt(1.0 + q * q);
+    }
+    float nx = 0.f, ny = 0.f;  // f32.Point{} when |d| < 1e-5
+    if (!(fabs(d) < 1e-5)) {
+        const float sc = line_width / (float)d;
+        nx = rx * sc, ny = ry * sc;
+    }
+    q0 = make_float4(s.x + nx, s.y + ny, s.z + nx, s.w + ny);
+    q1 = make_float4(s.z - nx, s.w - ny, s.x - nx, s.y - ny);
 }
 
-// Scatter: one block per kSegBlock particles (the unit segment_count_kernel counted).  Every warp owns 512 consecutive
-// particles of the block.  It loads their flag bytes and those of the row above once (16 bytes per lane), keeps them in
-// shared memory and counts the sticks as the count kernel does; one block barrier turns the eight warp totals into warp
-// offsets, and from there on the warps run independently: 32 particles per trip, flags from shared memory, the coordinate
-// loads of the next trip in flight while this trip's sticks are ranked with two ballots, converted and staged in a
-// warp-private buffer at their rank, then copied out as ONE contiguous, fully coalesced run of float4 (before ranking the
-// sticks of consecutive lanes are not adjacent in the output: a lane has 0, 1 or 2 of them).
-template <typename T>
+// One block per kSegBlock particles of the owned rows in PADDED row-major order (padding columns hold zero flags and add
+// nothing, so the order of the listed sticks is the unpadded one); blocks take their index from a ticket counter, so a
+// block's predecessors are always running or done.  Every warp owns 512 consecutive particles.  It loads their flag
+// bytes and those of the row above once (16 bytes per lane), keeps them in shared memory and counts the sticks with
+// byte-parallel tests: tail t lists its vertical stick when t and the particle above are active and that particle's
+// ALIVE_V bit is set, its horizontal stick likewise with the particle to the left.  Warp 0 publishes the block's count,
+// sums the counts of the blocks before it (decoupled look-back, 32 blocks per step) and publishes the inclusive prefix;
+// from there on the warps run independently: 32 particles per trip, flags from shared memory, the coordinate loads of
+// the next trip in flight while this trip's sticks are ranked with two ballots, converted and staged in a warp-private
+// buffer at their rank, then copied out as ONE contiguous, fully coalesced run (before ranking the sticks of consecutive
+// lanes are not adjacent in the output: a lane has 0, 1 or 2 of them).  QUADS: the run is written as outline quads
+// (2 float4 per stick, addSegment) instead of endpoint pairs.
+template <typename T, bool QUADS>
 __global__ void __launch_bounds__(kStreamThreads)
-    segment_write_kernel(Planes<T> P, Geom g, int cloth, const unsigned int* __restrict__ block_offsets,
-                         float4* __restrict__ xyxy, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
-                         unsigned long long cap) {
+    segment_export_kernel(Planes<T> P, Geom g, int cloth, unsigned long long* __restrict__ status, unsigned long long* ticket,
+                          unsigned long long ticket_base, unsigned int epoch, unsigned int n_blocks, float line_width,
+                          float4* __restrict__ out, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
+                          unsigned long long cap, unsigned long long* __restrict__ total_out) {
     constexpr int kWarps = kStreamThreads / 32, kPerWarp = kSegBlock / kWarps, kTrips = kPerWarp / 32;
     static_assert(kPerWarp == 32 * 16, "one uint4 of flag bytes per lane");
     __shared__ unsigned int warp_tot[kWarps];
+    __shared__ unsigned int s_bid;
+    __shared__ unsigned long long s_excl;
     __shared__ __align__(16) uint8_t s_f[kWarps][kPerWarp + 16];   // [15] = the particle left of the warp's first one
     __shared__ __align__(16) uint8_t s_fu[kWarps][kPerWarp];
     __shared__ float4 s_xy[kWarps][64];
@@ -361,12 +311,15 @@ __global__ void __launch_bounds__(kStreamThreads)
     const long long base = (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t below = (1u << lane) - 1u;
-    const long long warp_first = (long long)blockIdx.x * kSegBlock + (long long)w * kPerWarp;
+    if (threadIdx.x == 0) s_bid = (unsigned int)(atomicAdd(ticket, 1ull) - ticket_base);
+    __syncthreads();
+    const unsigned int bid = s_bid;
+    const long long warp_first = (long long)bid * kSegBlock + (long long)w * kPerWarp;
     const uint8_t* fl = P.fl + base;
     const T* X = P.x + base;
     const T* Y = P.y + base;
 
-    {   // ---- flags of this warp's 512 particles -> shared memory; their sticks (segment_count_kernel's tests) -----------
+    {   // ---- flags of this warp's 512 particles -> shared memory; their sticks ---------------------------------------------
         constexpr uint32_t k1 = 0x01010101u;
         const long long off = warp_first + lane * 16;
         unsigned int cnt = 0;
@@ -375,14 +328,14 @@ __global__ void __launch_bounds__(kStreamThreads)
         if (off < n) {
             const int ly = (int)(off / g.pitch), cx = (int)(off - (long long)ly * g.pitch);
             w4 = *reinterpret_cast<const uint4*>(fl + off);
-            if (g.own_row0 + ly > g.held_row0) u4 = *reinterpret_cast<const uint4*>(fl + off - g.pitch);
+            if (g.own_row0 + ly > g.held_row0) u4 = *reinterpret_cast<const uint4*>(fl + off - g.pitch);  // a ghost row of a strip, or absent at the cloth's top
             if (cx > 0) left = fl[off - 1];
             const uint32_t wq[4] = {w4.x, w4.y, w4.z, w4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
-            uint32_t carry = left;
+            uint32_t carry = left;  // flag byte of the particle left of word q
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t f = wq[q], act = (f >> 1) & k1;
-                const uint32_t fl_left = (f << 8) | (carry & 0xffu);
+                const uint32_t fl_left = (f << 8) | (carry & 0xffu);  // each byte: the flags of its left neighbour
                 cnt += __popc(act & (up[q] >> 4) & (up[q] >> 1) & k1) + __popc(act & (fl_left >> 3) & (fl_left >> 1) & k1);
                 carry = f >> 24;
             }
@@ -394,13 +347,6 @@ __global__ void __launch_bounds__(kStreamThreads)
         if (lane == 0) warp_tot[w] = cnt;
     }
     __syncthreads();
-    // (output positions fit 32 bits: the host side rejects cloths with 2^32 or more possible sticks)
-    unsigned int run = block_offsets[blockIdx.x];
-    for (int k = 0; k < w; ++k) run += warp_tot[k];
-    const unsigned int cap32 = (unsigned int)min(cap, 0xffffffffull);
-    const unsigned int run0 = run, hl_shift = run0 & 15u;  // (hl itself is 16-byte aligned)
-    unsigned int hl_at = hl_shift;                         // where this trip's highlight bytes go in s_hl[w]
-
     // rows and columns in 32-bit arithmetic: one division per lane, then every trip advances the lane by 32 particles
     const int row0 = (int)(warp_first / g.pitch), cx0 = (int)(warp_first - (long long)row0 * g.pitch);
     const int n_here = (int)min((long long)kPerWarp, n - warp_first);  // particles of this warp (<= 0: none)
@@ -440,7 +386,53 @@ __global__ void __launch_bounds__(kStreamThreads)
         return t;
     };
 
-    Trip cur = fetch(0);
+    Trip cur = fetch(0);  // in flight during the look-back below
+    if (w == 0) {   // ---- decoupled look-back: where this block's sticks start in the list ------------------------------------
+        unsigned long long block_total = 0;
+        for (int k = 0; k < kWarps; ++k) block_total += warp_tot[k];
+        volatile unsigned long long* st = status;
+        if (lane == 0) {
+            st[bid] = seg_status(epoch, bid == 0 ? kSegFlagPrefix : kSegFlagAggregate, block_total);
+            __threadfence();
+        }
+        unsigned long long excl = 0;
+        long long look = (long long)bid - 1;  // nearest predecessor this step looks at (lane 0)
+        while (look >= 0) {
+            const long long at = look - lane;
+            unsigned long long word = seg_status(epoch, kSegFlagPrefix, 0);  // before block 0: an empty prefix
+            if (at >= 0) word = st[at];
+            const bool valid = (unsigned int)(word >> 35) == (epoch & 0x1fffffffu) && ((word >> 33) & 3ull) != 0ull;
+            const bool is_prefix = valid && ((word >> 33) & 3ull) == kSegFlagPrefix;
+            const uint32_t bp = __ballot_sync(0xffffffffu, is_prefix), binv = __ballot_sync(0xffffffffu, !valid);
+            const int first_p = bp ? __ffs(bp) - 1 : 32;
+            const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
+            if (binv & need) {  // a block this step depends on has not published yet
+                __nanosleep(32);
+                continue;
+            }
+            unsigned long long v = (lane <= first_p) ? (word & 0x1ffffffffull) : 0ull;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            excl += __shfl_sync(0xffffffffu, v, 0);
+            if (first_p < 32) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            if (bid != 0) {
+                st[bid] = seg_status(epoch, kSegFlagPrefix, excl + block_total);
+                __threadfence();
+            }
+            s_excl = excl;
+            if (bid + 1 == n_blocks) *total_out = excl + block_total;
+        }
+    }
+    __syncthreads();
+    // (output positions fit 32 bits: the host side rejects cloths with 2^32 or more possible sticks)
+    unsigned int run = (unsigned int)s_excl;
+    for (int k = 0; k < w; ++k) run += warp_tot[k];
+    const unsigned int cap32 = (unsigned int)min(cap, 0xffffffffull);
+    const unsigned int run0 = run, hl_shift = run0 & 15u;  // (hl itself is 16-byte aligned)
+    unsigned int hl_at = hl_shift;                         // where this trip's highlight bytes go in s_hl[w]
+
 #pragma unroll 1
     for (int trip = 0; trip < kTrips; ++trip) {
         if (trip * 32 >= n_here) break;  // warp-uniform
@@ -459,21 +451,27 @@ __global__ void __launch_bounds__(kStreamThreads)
             if (v) {
                 s_xy[w][r] = make_float4((float)cur.xu, (float)cur.yu, x2, y2);
                 s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 8)) != 0;  // cloth.go:127-128: both ends highlighted
-                s_idx[w][r] = make_uint2(cur.tail - g.nx, cur.tail);
+                if (!QUADS) s_idx[w][r] = make_uint2(cur.tail - g.nx, cur.tail);
                 ++r;
             }
             if (h) {
                 s_xy[w][r] = make_float4(xl, yl, x2, y2);
                 s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 16)) != 0;
-                s_idx[w][r] = make_uint2(cur.tail - 1, cur.tail);
+                if (!QUADS) s_idx[w][r] = make_uint2(cur.tail - 1, cur.tail);
             }
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const unsigned int j = q * 32 + lane, o = run + j;
                 if (j < total && o < cap32) {
-                    xyxy[o] = s_xy[w][j];
-                    if (idx) idx[o] = s_idx[w][j];
+                    if (QUADS) {
+                        float4 q0, q1;
+                        segment_quad(s_xy[w][j], line_width, q0, q1);
+                        out[2ull * o] = q0, out[2ull * o + 1] = q1;
+                    } else {
+                        out[o] = s_xy[w][j];
+                        if (idx) idx[o] = s_idx[w][j];
+                    }
                 }
             }
             __syncwarp();  // the staging buffer is rewritten by the next trip
@@ -492,39 +490,6 @@ __global__ void __launch_bounds__(kStreamThreads)
             for (unsigned int b = 0; b < 16u; ++b)
                 if (c + b >= hl_shift && c + b < hl_at && o + b < cap32) hl[o + b] = s_hl[w][c + b];
         }
-    }
-}
-
-// addSegment / normal of the reference's render loops (physics/cloth.go:150-168) on the compacted live-stick list: for every
-// stick the four float32 corners {a+n, b+n, b-n, a-n} of its outline quad, n = the stick's normal scaled to the line
-// width.  math.Hypot is max * sqrt(1 + (min/max)^2) in binary64 (hypot_amd64.s); everything else is float32 arithmetic,
-// one rounding per operation (-fmad=false, IEEE division).  One thread per stick: 16 bytes in, 32 bytes out.
-__global__ void __launch_bounds__(kStreamThreads)
-    segment_quads_kernel(const float4* __restrict__ xyxy, const unsigned long long* __restrict__ total, float line_width,
-                         float4* __restrict__ quads, unsigned long long cap) {
-    const unsigned long long n = min(*total, cap);
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const float4 s = xyxy[i];  // a = (s.x, s.y), b = (s.z, s.w)
-        const float dx = s.z - s.x, dy = s.w - s.y;  // dir := b.Sub(a)
-        const float rx = +dy, ry = -dx;              // dir.X, dir.Y = +dir.Y, -dir.X
-        double p = fabs((double)rx), q = fabs((double)ry);
-        if (p < q) {
-            const double t = p;
-            p = q, q = t;
-        }
-        double d = 0.0;
-        if (p != 0.0) {
-            q = q / p;
-            d = p * sqrt(1.0 + q * q);
-        }
-        float nx = 0.f, ny = 0.f;  // f32.Point{} when |d| < 1e-5
-        if (!(fabs(d) < 1e-5)) {
-            const float sc = line_width / (float)d;
-            nx = rx * sc, ny = ry * sc;
-        }
-        quads[2 * i] = make_float4(s.x + nx, s.y + ny, s.z + nx, s.w + ny);
-        quads[2 * i + 1] = make_float4(s.z - nx, s.w - ny, s.x - nx, s.y - ny);
     }
 }
 

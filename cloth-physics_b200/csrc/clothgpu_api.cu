@@ -124,13 +124,13 @@ struct clothgpu {
     } link[2];                       // 0 = upper neighbour, 1 = lower neighbour
     unsigned int epoch = 0;          // operations (fused launches, pushes) done since attach
     // scratch for segment export
-    unsigned int* seg_counts = nullptr;
-    size_t seg_counts_cap = 0;
-    void* seg_out = nullptr;
+    unsigned long long* seg_status = nullptr;  // look-back status word per block of the export kernel (never cleared: epoch-tagged)
+    size_t seg_status_cap = 0;
+    void* seg_out = nullptr;                   // per possible stick: 32 B (quads, or endpoints + indices) + 1 highlight byte
     size_t seg_out_cap = 0;
-    unsigned long long* seg_total = nullptr;
-    void* seg_quads = nullptr;  // 2 float4 per stick, allocated on the first clothgpu_read_quads_f32
-    size_t seg_quads_cap = 0;
+    unsigned long long* seg_total = nullptr;   // [0] sticks listed by the last export, [1] the export kernel's block ticket
+    unsigned long long seg_ticket_base = 0;    // blocks launched by all exports so far (the ticket only grows)
+    unsigned int seg_epoch = 0;
 };
 
 namespace {
@@ -676,10 +676,9 @@ void free_all(clothgpu* c) {
     cudaFreeHost(c->ctr_host);
     cudaFree(c->frames_dev);
     cudaFreeHost(c->frames_host);
-    cudaFree(c->seg_counts);
+    cudaFree(c->seg_status);
     cudaFree(c->seg_out);
     cudaFree(c->seg_total);
-    cudaFree(c->seg_quads);
     if (c->frames_copied) cudaEventDestroy(c->frames_copied);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -856,9 +855,9 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     alloc((void**)&c->ctr_base, 2 * sizeof(DevCounters));
     c->ctr = c->ctr_base;
     alloc((void**)&c->census, 5 * sizeof(unsigned long long));
-    alloc((void**)&c->seg_total, sizeof(unsigned long long));
+    alloc((void**)&c->seg_total, 2 * sizeof(unsigned long long));
     if (rc == CLOTHGPU_OK) {
-        cudaError_t ee = cudaMallocHost((void**)&c->ctr_host, 2 * sizeof(DevCounters) + 5 * sizeof(unsigned long long));
+        cudaError_t ee = cudaMallocHost((void**)&c->ctr_host, 2 * sizeof(DevCounters) + 6 * sizeof(unsigned long long));  // + the export's total
         if (ee != cudaSuccess) rc = fail(CLOTHGPU_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(ee));
     }
     const size_t fbytes = sizeof(FrameU<double>) * (size_t)ensemble;
@@ -1177,55 +1176,98 @@ int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* act
 }
 
 namespace {
-// Live-stick compaction on the handle's stream: per-block counts, exclusive scan, ballot-ranked scatter into c->seg_out.
-int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, size_t* max_sticks_out) {
+// Live-stick export on the handle's stream: ONE launch (per-block counts, decoupled look-back, ballot-ranked scatter) into
+// c->seg_out.  quads = false: float4 endpoints at [0, n), optional uint2 indices behind them; quads = true: 2 float4 of
+// outline per stick.  Highlight bytes behind the 32 B/stick area in both cases.
+int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float line_width, size_t* max_sticks_out) {
     if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
     const Geom& g = c->g;
     const long long n = (long long)g.nx * g.own_rows;
     const long long padded = (long long)g.pitch * g.own_rows;
-    const unsigned blocks = (unsigned)((padded + kSegBlock - 1) / kSegBlock);                         // scatter blocks
-    const unsigned count_blocks = blocks;  // 256 threads x 16 flag bytes = the particles of one scatter block
-    if (c->seg_counts_cap < blocks) {
-        cudaFree(c->seg_counts);
-        c->seg_counts = nullptr;
-        CU_TRY(cudaMalloc((void**)&c->seg_counts, (size_t)blocks * sizeof(unsigned int)));
-        c->seg_counts_cap = blocks;
+    const unsigned blocks = (unsigned)std::max<long long>(1, (padded + kSegBlock - 1) / kSegBlock);
+    if (c->seg_status_cap < blocks) {
+        cudaFree(c->seg_status);
+        c->seg_status = nullptr;
+        c->seg_status_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->seg_status, (size_t)blocks * sizeof(unsigned long long)));
+        CU_TRY(cudaMemsetAsync(c->seg_status, 0, (size_t)blocks * sizeof(unsigned long long), c->stream));
+        c->seg_status_cap = blocks;
+        c->seg_epoch = 0;
     }
-    const size_t per = sizeof(float4) + sizeof(uint2) + 1;
     const size_t max_sticks = (size_t)2 * n;
-    if (max_sticks > 0xffffffffull)  // the scan and the scatter kernel keep output positions in 32 bits
+    if (max_sticks > 0xffffffffull)  // the look-back and the scatter keep output positions in 32 bits
         return fail(CLOTHGPU_ERR_INVALID, "live-stick compaction supports cloths of up to 2^31 particles");
     if (c->seg_out_cap < max_sticks) {
         cudaFree(c->seg_out);
         c->seg_out = nullptr;
-        CU_TRY(cudaMalloc(&c->seg_out, max_sticks * per));
+        c->seg_out_cap = 0;
+        CU_TRY(cudaMalloc(&c->seg_out, std::max<size_t>(1, max_sticks) * 33 + 64));
         c->seg_out_cap = max_sticks;
     }
-    float4* d_xyxy = (float4*)c->seg_out;
-    uint2* d_idx = (uint2*)(d_xyxy + max_sticks);
-    uint8_t* d_hl = (uint8_t*)(d_idx + max_sticks);
+    float4* d_main = (float4*)c->seg_out;
+    uint2* d_idx = (uint2*)(d_main + max_sticks);
+    uint8_t* d_hl = (uint8_t*)(d_main + 2 * max_sticks);
+    c->seg_epoch = (c->seg_epoch + 1) & 0x1fffffffu;
+    if (c->seg_epoch == 0) {  // the 29-bit epoch wrapped: forget the old status words once
+        CU_TRY(cudaMemsetAsync(c->seg_status, 0, c->seg_status_cap * sizeof(unsigned long long), c->stream));
+        c->seg_epoch = 1;
+    }
     auto run = [&](auto tag) {
         using T = decltype(tag);
         Planes<T> P = planes<T>(c, c->cur_pos, c->cur_prev);
-        segment_count_kernel<T><<<count_blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts);
-        segment_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_counts, (int)blocks, c->seg_total);
-        segment_write_kernel<T><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_counts, d_xyxy, d_hl,
-                                                                           with_idx ? d_idx : nullptr, max_sticks);
+        if (quads)
+            segment_export_kernel<T, true><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_status, c->seg_total + 1, c->seg_ticket_base,
+                                                                                     c->seg_epoch, blocks, line_width, d_main, d_hl, nullptr,
+                                                                                     max_sticks, c->seg_total);
+        else
+            segment_export_kernel<T, false><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_status, c->seg_total + 1, c->seg_ticket_base,
+                                                                                      c->seg_epoch, blocks, 0.f, d_main, d_hl, with_idx ? d_idx : nullptr,
+                                                                                      max_sticks, c->seg_total);
     };
     if (c->precision == CLOTHGPU_F32)
         run(float{});
     else
         run(double{});
     CU_TRY(cudaGetLastError());
-    c->launches += 3;
+    c->seg_ticket_base += blocks;
+    c->launches += 1;
     if (max_sticks_out) *max_sticks_out = max_sticks;
+    return CLOTHGPU_OK;
+}
+
+// Copy an export back.  Small lists (GUI-sized cloths) are copied at the caller's full capacity together with the count
+// and synchronised once — the count is then only checked afterwards; large ones wait for the count and copy exactly n.
+struct ExportCopy {
+    void* dst;
+    const void* src;
+    size_t bytes_per_stick;
+};
+int copy_export(clothgpu* c, size_t max_sticks, size_t cap, const ExportCopy* copies, int n_copies, size_t* n_out) {
+    unsigned long long* total_host = (unsigned long long*)(c->ctr_host + 2 * sizeof(DevCounters) + 5 * sizeof(unsigned long long));
+    CU_TRY(cudaMemcpyAsync(total_host, c->seg_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    bool any = false;
+    for (int k = 0; k < n_copies; ++k) any = any || copies[k].dst != nullptr;
+    const size_t spec = std::min(cap, max_sticks);
+    const bool speculative = any && spec * 33 <= (size_t)(4u << 20);
+    if (speculative)
+        for (int k = 0; k < n_copies; ++k)
+            if (copies[k].dst && spec)
+                CU_TRY(cudaMemcpyAsync(copies[k].dst, copies[k].src, spec * copies[k].bytes_per_stick, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned long long total = *total_host;
+    *n_out = (size_t)total;
+    if (!any) return CLOTHGPU_OK;  // count only
+    if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
+    if (!speculative && total)
+        for (int k = 0; k < n_copies; ++k)
+            if (copies[k].dst) CU_TRY(cudaMemcpy(copies[k].dst, copies[k].src, (size_t)total * copies[k].bytes_per_stick, cudaMemcpyDeviceToHost));
     return CLOTHGPU_OK;
 }
 }  // namespace
 
 int clothgpu_compact_segments(clothgpu* c, int32_t cloth) {
     if (int rc = check_handle(c)) return rc;
-    return compact_enqueue(c, cloth, false, nullptr);
+    return compact_enqueue(c, cloth, false, false, 0.f, nullptr);
 }
 
 int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t* highlighted,
@@ -1233,22 +1275,12 @@ int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t*
     if (int rc = check_handle(c)) return rc;
     if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
     size_t max_sticks = 0;
-    if (int rc = compact_enqueue(c, cloth, sticks_idx != nullptr, &max_sticks)) return rc;
-    float4* d_xyxy = (float4*)c->seg_out;
-    uint2* d_idx = (uint2*)(d_xyxy + max_sticks);
-    uint8_t* d_hl = (uint8_t*)(d_idx + max_sticks);
-    unsigned long long total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, c->seg_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    *n_out = (size_t)total;
-    if (!xyxy && !highlighted && !sticks_idx) return CLOTHGPU_OK;  // count only
-    if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
-    if (total) {
-        if (xyxy) CU_TRY(cudaMemcpy(xyxy, d_xyxy, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost));
-        if (highlighted) CU_TRY(cudaMemcpy(highlighted, d_hl, (size_t)total, cudaMemcpyDeviceToHost));
-        if (sticks_idx) CU_TRY(cudaMemcpy(sticks_idx, d_idx, (size_t)total * sizeof(uint2), cudaMemcpyDeviceToHost));
-    }
-    return CLOTHGPU_OK;
+    if (int rc = compact_enqueue(c, cloth, sticks_idx != nullptr, false, 0.f, &max_sticks)) return rc;
+    float4* d_main = (float4*)c->seg_out;
+    const ExportCopy copies[3] = {{xyxy, d_main, sizeof(float4)},
+                                  {highlighted, (uint8_t*)(d_main + 2 * max_sticks), 1},
+                                  {sticks_idx, (uint2*)(d_main + max_sticks), sizeof(uint2)}};
+    return copy_export(c, max_sticks, cap, copies, 3, n_out);
 }
 
 int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float* quads, uint8_t* highlighted,
@@ -1257,35 +1289,10 @@ int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float*
     if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
     if (!(line_width >= 0.f) || !(line_width <= 1e30f)) return fail(CLOTHGPU_ERR_INVALID, "line width must be finite and >= 0");
     size_t max_sticks = 0;
-    if (int rc = compact_enqueue(c, cloth, false, &max_sticks)) return rc;
-    float4* d_xyxy = (float4*)c->seg_out;
-    uint8_t* d_hl = (uint8_t*)((uint2*)(d_xyxy + max_sticks) + max_sticks);
-    if (quads) {
-        if (c->seg_quads_cap < max_sticks) {
-            cudaFree(c->seg_quads);
-            c->seg_quads = nullptr;
-            c->seg_quads_cap = 0;
-            CU_TRY(cudaMalloc(&c->seg_quads, max_sticks * 2 * sizeof(float4)));
-            c->seg_quads_cap = max_sticks;
-        }
-        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((max_sticks + kStreamThreads - 1) / kStreamThreads,
-                                                                             (size_t)c->sm_count * 16));
-        segment_quads_kernel<<<grid, kStreamThreads, 0, c->stream>>>(d_xyxy, c->seg_total, line_width, (float4*)c->seg_quads,
-                                                                      (unsigned long long)max_sticks);
-        CU_TRY(cudaGetLastError());
-        c->launches++;
-    }
-    unsigned long long total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, c->seg_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    *n_out = (size_t)total;
-    if (!quads && !highlighted) return CLOTHGPU_OK;  // count only
-    if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
-    if (total) {
-        if (quads) CU_TRY(cudaMemcpy(quads, c->seg_quads, (size_t)total * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
-        if (highlighted) CU_TRY(cudaMemcpy(highlighted, d_hl, (size_t)total, cudaMemcpyDeviceToHost));
-    }
-    return CLOTHGPU_OK;
+    if (int rc = compact_enqueue(c, cloth, false, true, line_width, &max_sticks)) return rc;
+    float4* d_main = (float4*)c->seg_out;
+    const ExportCopy copies[2] = {{quads, d_main, 2 * sizeof(float4)}, {highlighted, (uint8_t*)(d_main + 2 * max_sticks), 1}};
+    return copy_export(c, max_sticks, cap, copies, 2, n_out);
 }
 
 int clothgpu_get_counters(clothgpu* c, clothgpu_counters* out) {
