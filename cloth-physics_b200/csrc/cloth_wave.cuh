@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     if (r_start >= g.own_rows) continue;  // the padding unit of an odd-height cloth
     const int e = colidx / pl.bands;
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
-    const bool dragging = DRAG && (u.buttons & CLOTHGPU_MOUSE_DRAGGING) != 0;
+    const bool dragging = DRAG && ((PACK && PER_CLOTH) || (u.buttons & CLOTHGPU_MOUSE_DRAGGING) != 0);
 
     // ---- band (columns) and chunk (rows) ---------------------------------------------------------------------------
     const int bx = colidx % pl.bands;
@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
     auto live_bit = [](uint32_t fh, uint32_t ft, uint32_t alive) -> uint32_t {
         return ((fh & alive) && (fh & ft & CLOTHGPU_FLAG_ACTIVE)) ? 1u : 0u;  // cloth.go:97
     };
+    // (tear4: packed ensembles with one frame block per cloth — bits 12..15 say which of the block's four sticks belong to
+    //  a cloth that is being dragged, in the order of the live bits)
     auto pack = [&](uint32_t fa, uint32_t fb, uint32_t fc, uint32_t fd, uint32_t first_alive, uint32_t second_alive,
-                    bool first_ok) -> uint32_t {
+                    bool first_ok, uint32_t tear4 = 0u) -> uint32_t {
         uint32_t st = 0;
         if (first_ok) st |= live_bit(fa, fb, first_alive) | (live_bit(fc, fd, first_alive) << 1);
         st |= (live_bit(fa, fc, second_alive) << 2) | (live_bit(fb, fd, second_alive) << 3);
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                        pd = fd & CLOTHGPU_FLAG_PIN;  // CLOTHGPU_FLAG_PIN == 1
         st |= (pa << 4) | (pb << 5) | (pc << 6) | (pd << 7);
         st |= (pa << 8) | (pc << 9) | (pb << 10) | (pd << 11);
+        st |= tear4 << 12;
         return st;
     };
 
@@ -258,6 +261,24 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
         const int col_end = PACK ? pl.nx : cols;  // the pair's first column exists iff pk_cc < col_end
         int pk_lr = 2, pk_m = 0, pk_rr = 0;  // packed ensembles: local row 2q of the pair being delivered = row pk_rr of cloth pair pk_m
         if (PACK) pk_m = y0 / pl.rows_v, pk_rr = y0 - pk_m * pl.rows_v;
+        // Packed ensembles with one frame block per cloth: the entry warps work with the frame of the cloth their column
+        // half of the pair being delivered belongs to (reloaded when the pair moves on to the next cloth); the sweeps only
+        // need what the host checked to be common to all cloths (rest length, gain, tear length) plus, per stick, whether
+        // its cloth is being dragged — that goes into the block state words.
+        // (the frame is read through the pointer where it is used — all threads of a half read the same words, they stay in
+        //  L1 — instead of 40 more live registers per entry thread)
+        constexpr bool kPerClothPack = PACK && PER_CLOTH;
+        const FrameU<T>* uep = per_cloth;  // only dereferenced when kPerClothPack
+        uint32_t dr_own = dragging ? 1u : 0u, dr_other = dr_own, dr_prev = dr_own;
+        int ue_m = -1;  // cloth pair `uep` belongs to
+        auto cloth_frame = [&](int m) {
+            if (!kPerClothPack || m == ue_m) return;
+            ue_m = m;
+            const int own = min(2 * m + pk_half, pl.ensemble - 1), other = min(2 * m + 1 - pk_half, pl.ensemble - 1);
+            uep = per_cloth + own;
+            dr_own = (uep->buttons & CLOTHGPU_MOUSE_DRAGGING) ? 1u : 0u;
+            dr_other = (per_cloth[other].buttons & CLOTHGPU_MOUSE_DRAGGING) ? 1u : 0u;
+        };
         struct RowAt {
             long long at;   // element offset of (row, first column of the pair)
             bool ok;        // the row exists (and the pair's first column with it)
@@ -391,6 +412,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 } else {
                     cp_async_wait<kWaveDepth - 1>();
                 }
+                cloth_frame(pk_m);  // (pk_m: the cloth pair of the pair being delivered)
+                const bool drag_e = kPerClothPack ? dr_own != 0u : dragging;
                 const uint32_t fkeep = (PACK || pk_cc + 1 < col_end) ? 0xffffu : 0xffu;
                 const uint32_t fcur[2] = {fnext[0] & fkeep, fnext[1] & fkeep};
                 fnext[0] = load_flags(q + 1, 0), fnext[1] = load_flags(q + 1, 1);
@@ -411,8 +434,13 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     if (ra_.ok) {
                         T px0 = vpx.x, px1 = vpx.y, py0 = vpy.x, py1 = vpy.y;
                         const uint32_t f0_in = f0[row], f1_in = f1[row];
-                        particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], u);
-                        if (pk_cc + 1 < col_end) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
+                        if (kPerClothPack) {
+                            particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], *uep);
+                            if (pk_cc + 1 < col_end) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], *uep);
+                        } else {
+                            particle_update(p0[row].x, p0[row].y, px0, py0, f0[row], u);
+                            if (pk_cc + 1 < col_end) particle_update(p1[row].x, p1[row].y, px1, py1, f1[row], u);
+                        }
                         if (owned(lr, c)) {  // the owner of a particle writes its previous position
                             events.note2(f0_in & 0x1fu, f0[row] & 0x1fu, f1_in & 0x1fu, f1[row] & 0x1fu);
                             const long long at = ra_.at;
@@ -449,7 +477,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                         pins |= ((f0[w] & CLOTHGPU_FLAG_PIN) | ((f1[w] & CLOTHGPU_FLAG_PIN) << 1)) << (2 * w);
                     }
                     bool touched = false;
-                    const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, dragging, touched);
+                    // (the sticks only read what all cloths share — rest length, gain, tear length — so `u` serves every cloth)
+                    const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, drag_e, touched);
                     if (DRAG && tore) {
 #pragma unroll
                         for (int w = 0; w < 2; ++w)
@@ -473,19 +502,26 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 {   // group A, pair q: rows (2q, 2q+1) x columns (2et+1, 2et+2); heads a (H, V), c (H), b (V)
                     const int er = (et + 1) & (HW - 1), cl = c + 1, cr = 2 * er;
                     const uint32_t fb = fl8[eslot * TW + cr], fd = fl8[(eslot + 1) * TW + cr];
-                    const uint32_t st = pack(f1[0], fb, f1[1], fd, CLOTHGPU_FLAG_ALIVE_H, CLOTHGPU_FLAG_ALIVE_V, et + 1 < HW);
+                    // heads: a (H-odd, V-even), c (H-odd): this thread's odd column; b (V-even): the even column to the right,
+                    // which belongs to the other cloth of the pair when it lies in the other half of the band
+                    const uint32_t dr_b = (er >> 6) == pk_half ? dr_own : dr_other;
+                    const uint32_t tearA = kPerClothPack ? (dr_own | (dr_own << 1) | (dr_own << 2) | (dr_b << 3)) : 0u;
+                    const uint32_t st = pack(f1[0], fb, f1[1], fd, CLOTHGPU_FLAG_ALIVE_H, CLOTHGPU_FLAG_ALIVE_V, et + 1 < HW, tearA);
                     stA[(eslot >> 1) * HW + et] = (uint16_t)st;
                     const bool oa = owned(2 * q, cl), oc = owned(2 * q + 1, cl), ob = owned(2 * q, cr);
                     acc_live += (oa ? (st & 1u) + ((st >> 2) & 1u) : 0u) + (oc ? (st >> 1) & 1u : 0u) + (ob ? (st >> 3) & 1u : 0u);
                 }
                 {   // group B, pair q-1: rows (2q-1, 2q) x columns (2et, 2et+1); heads a (V, H), c (V), b (H)
                     const int s2p = eslot == 0 ? RB - 2 : eslot - 2;  // slot of row 2(q-1)
-                    const uint32_t st = pack(fprev[0], f0[0], fprev[1], f1[0], CLOTHGPU_FLAG_ALIVE_V, CLOTHGPU_FLAG_ALIVE_H, true);
+                    // heads: a (V-odd, H-even), c (V-odd): row 2q-1, the cloth of the previous pair; b (H-even): row 2q
+                    const uint32_t tearB = kPerClothPack ? (dr_prev | (dr_prev << 1) | (dr_prev << 2) | (dr_own << 3)) : 0u;
+                    const uint32_t st = pack(fprev[0], f0[0], fprev[1], f1[0], CLOTHGPU_FLAG_ALIVE_V, CLOTHGPU_FLAG_ALIVE_H, true, tearB);
                     stB[(s2p >> 1) * HW + et] = (uint16_t)st;
                     const bool oa = owned(2 * q - 1, c), oc = owned(2 * q - 1, c + 1), ob = owned(2 * q, c);
                     acc_live += (oa ? (st & 1u) + ((st >> 2) & 1u) : 0u) + (oc ? (st >> 1) & 1u : 0u) + (ob ? (st >> 3) & 1u : 0u);
                 }
                 fprev[0] = f0[1], fprev[1] = f1[1];
+                dr_prev = dr_own;
             }
             if (kWaveSets == 2) {
                 // The pair delivered in step s is first read in step s + 1, and nothing it writes is touched by set X
@@ -543,7 +579,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             V2 pa[NI], pb[NI], pc[NI], pd[NI];
             uint32_t st[NI];
             int sa[NI], pp[NI], jn[NI];
-            uint32_t live1 = 0, live2 = 0, pins1 = 0, pins2 = 0;
+            uint32_t live1 = 0, live2 = 0, pins1 = 0, pins2 = 0, tear1 = 0xffffffffu, tear2 = 0xffffffffu;
+            if (PACK && PER_CLOTH) tear1 = tear2 = 0u;
 #pragma unroll
             for (int n = 0; n < NI; ++n) {
                 const int i = i0 + n;
@@ -554,6 +591,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 const uint32_t sm = st[n] & maskA[i];
                 live1 |= (sm & 3u) << (2 * n), live2 |= ((sm >> 2) & 3u) << (2 * n);
                 pins1 |= ((st[n] >> 4) & 15u) << (4 * n), pins2 |= ((st[n] >> 8) & 15u) << (4 * n);
+                if (PACK && PER_CLOTH) tear1 |= ((st[n] >> 12) & 3u) << (2 * n), tear2 |= ((st[n] >> 14) & 3u) << (2 * n);
             }
             bool touched = false;
             uint32_t tore1 = 0, tore2 = 0;
@@ -564,14 +602,14 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     V2* tt[NS];
 #pragma unroll
                     for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
-                    tore1 = relax_n<T, DRAG, NS, PM>(hh, tt, live1, pins1, u, dragging, touched);
+                    tore1 = relax_n<T, DRAG, NS, PM>(hh, tt, live1, pins1, u, dragging, touched, tear1);
                 }
                 {  // V-even: a->c and b->d
                     V2* hh[NS];
                     V2* tt[NS];
 #pragma unroll
                     for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
-                    tore2 = relax_n<T, DRAG, NS, PM>(hh, tt, live2, pins2, u, dragging, touched);
+                    tore2 = relax_n<T, DRAG, NS, PM>(hh, tt, live2, pins2, u, dragging, touched, tear2);
                 }
             };
             // pinned particles are rare (the cloth's pinned rows): one vote per item picks the pass code without pin logic
@@ -603,7 +641,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
             V2 pa[NI], pb[NI], pc[NI], pd[NI];
             uint32_t st[NI];
             int sa[NI], sb[NI], pp[NI], jn[NI];
-            uint32_t live1 = 0, live2 = 0, pins1 = 0, pins2 = 0;
+            uint32_t live1 = 0, live2 = 0, pins1 = 0, pins2 = 0, tear1 = 0xffffffffu, tear2 = 0xffffffffu;
+            if (PACK && PER_CLOTH) tear1 = tear2 = 0u;
             bool any_mid = false;  // some item still has an H-even pass to do (it is not the last sweep's)
 #pragma unroll
             for (int n = 0; n < NI; ++n) {
@@ -616,6 +655,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                 const uint32_t sm = st[n] & maskB[i];  // (the last sweep's mask has no second-pass bits)
                 live1 |= (sm & 3u) << (2 * n), live2 |= ((sm >> 2) & 3u) << (2 * n);
                 pins1 |= ((st[n] >> 4) & 15u) << (4 * n), pins2 |= ((st[n] >> 8) & 15u) << (4 * n);
+                if (PACK && PER_CLOTH) tear1 |= ((st[n] >> 12) & 3u) << (2 * n), tear2 |= ((st[n] >> 14) & 3u) << (2 * n);
                 any_mid |= jn[n] + 1 < K;
             }
             bool touched = false;
@@ -627,14 +667,14 @@ __global__ void __launch_bounds__(kWaveThreads, 1)
                     V2* tt[NS];
 #pragma unroll
                     for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pb[n], hh[2 * n + 1] = &pc[n], tt[2 * n + 1] = &pd[n];
-                    tore1 = relax_n<T, DRAG, NS, PM>(hh, tt, live1, pins1, u, dragging, touched);
+                    tore1 = relax_n<T, DRAG, NS, PM>(hh, tt, live1, pins1, u, dragging, touched, tear1);
                 }
                 if (any_mid) {  // H-even of the next sweep: a->c and b->d (warp-uniform)
                     V2* hh[NS];
                     V2* tt[NS];
 #pragma unroll
                     for (int n = 0; n < NI; ++n) hh[2 * n] = &pa[n], tt[2 * n] = &pc[n], hh[2 * n + 1] = &pb[n], tt[2 * n + 1] = &pd[n];
-                    tore2 = relax_n<T, DRAG, NS, PM>(hh, tt, live2, pins2, u, dragging, touched);
+                    tore2 = relax_n<T, DRAG, NS, PM>(hh, tt, live2, pins2, u, dragging, touched, tear2);
                 }
             };
             if (__any_sync(0xffffffffu, (pins1 | pins2) != 0u)) passes(pins_each_t{});

@@ -433,7 +433,8 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
 // side in the 256-column band, the pairs stacked on top of each other (cloth_wave.cuh, WavePlan::pack).
 static bool wave_packable(const clothgpu* c, bool per_cloth_frames) {
     const Geom& g = c->g;
-    return c->wave_pack && !per_cloth_frames && c->desc.strip_rows <= 0 && g.ensemble >= 2 && g.nx <= kWaveTW / 2 && g.own_rows == g.held_rows &&
+    (void)per_cloth_frames;  // (one frame block per cloth is fine: cloth_wave.cuh, kPerClothPack)
+    return c->wave_pack && c->desc.strip_rows <= 0 && g.ensemble >= 2 && g.nx <= kWaveTW / 2 && g.own_rows == g.held_rows &&
            (long long)((g.ensemble + 1) / 2) * ((g.own_rows + 1) & ~1) < (1ll << 30);
 }
 
@@ -495,7 +496,9 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
         kernel<<<grid, kWaveThreads, smem, c->stream>>>(in, out, g, pl, u, per_cloth, c->ctr, pup, pdn, ss);
         return cudaSuccess;
     };
-    if (pc)
+    if (pc && pl.pack)
+        CU_TRY(go(wave_frame_kernel<T, true, true, true>));
+    else if (pc)
         CU_TRY(go(wave_frame_kernel<T, true, true>));
     else if (pl.pack)
         CU_TRY(drag ? go(wave_frame_kernel<T, false, true, true>) : go(wave_frame_kernel<T, false, false, true>));
@@ -508,9 +511,9 @@ int launch_wave(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     c->cur_pos = nxt;
     c->cur_prev = nprev;
     c->last_kernel = std::is_same<T, double>::value
-                         ? (pc ? "wave_frame_kernel<double,PER_CLOTH>" : pl.pack ? (drag ? "wave_frame_kernel<double,DRAG,PACK>" : "wave_frame_kernel<double,PACK>")
+                         ? (pc ? (pl.pack ? "wave_frame_kernel<double,PER_CLOTH,PACK>" : "wave_frame_kernel<double,PER_CLOTH>") : pl.pack ? (drag ? "wave_frame_kernel<double,DRAG,PACK>" : "wave_frame_kernel<double,PACK>")
                                                                                  : drag ? "wave_frame_kernel<double,DRAG>" : "wave_frame_kernel<double>")
-                         : (pc ? "wave_frame_kernel<float,PER_CLOTH>" : pl.pack ? (drag ? "wave_frame_kernel<float,DRAG,PACK>" : "wave_frame_kernel<float,PACK>")
+                         : (pc ? (pl.pack ? "wave_frame_kernel<float,PER_CLOTH,PACK>" : "wave_frame_kernel<float,PER_CLOTH>") : pl.pack ? (drag ? "wave_frame_kernel<float,DRAG,PACK>" : "wave_frame_kernel<float,PACK>")
                                                                                 : drag ? "wave_frame_kernel<float,DRAG>" : "wave_frame_kernel<float>");
     return CLOTHGPU_OK;
 }
@@ -573,8 +576,9 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         if (c->desc.strip_rows > 0 && depth > c->ghost)
             return fail(CLOTHGPU_ERR_INVALID, "iterations=%d needs %d ghost rows, handle has %d (raise desc.max_iterations)",
                         K, depth, c->ghost);
-        if (per_cloth && K != (frames[0].iterations < 1 ? 1 : frames[0].iterations))
-            return fail(CLOTHGPU_ERR_INVALID, "per-cloth frames must share `iterations`");
+        if (per_cloth && (K != (frames[0].iterations < 1 ? 1 : frames[0].iterations) || f.tear_length != frames[0].tear_length ||
+                          f.relax_gain != frames[0].relax_gain))
+            return fail(CLOTHGPU_ERR_INVALID, "per-cloth frames must share `iterations`, `tear_length` and `relax_gain`");
     }
     const FrameU<T>* dev_frames = nullptr;
     FrameU<T> u0 = fold_frame<T>(frames[0], c->desc.spacing);

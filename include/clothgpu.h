@@ -193,7 +193,9 @@ CLOTHGPU_API int clothgpu_step(clothgpu* c, const clothgpu_frame* frame);
 /* n consecutive frames (headless loop); frames[i] is frame i. */
 CLOTHGPU_API int clothgpu_step_n(clothgpu* c, const clothgpu_frame* frames, int32_t n);
 
-/* Ensemble handles only: frames[e] drives cloth e (e < ensemble) for one frame. */
+/* Ensemble handles only: frames[e] drives cloth e (e < ensemble) for one frame.  The frames may differ in everything the
+ * particle loop reads (mouse, buttons, sliders, window, dt); `iterations`, `tear_length` and `relax_gain` must be the
+ * same for all cloths (CLOTHGPU_ERR_INVALID otherwise). */
 CLOTHGPU_API int clothgpu_step_each(clothgpu* c, const clothgpu_frame* frames, int32_t count);
 
 /* Block until everything queued on the handle has finished. */

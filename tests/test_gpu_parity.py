@@ -535,3 +535,61 @@ def test_strips_multi_gpu_nccl():
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run_strip_worker(min(n, 8), ["--backend", "nccl", "--nx", "1024", "--ny", "1024", "--iterations", "8", "--frames", "6"])
+
+
+@pytest.mark.parametrize("nx,ny,E,K", [(128, 128, 6, 8), (100, 91, 7, 8), (64, 40, 9, 4), (17, 300, 3, 5), (128, 130, 5, 6)])
+def test_packed_ensembles_with_one_frame_per_cloth(oracle, nx, ny, E, K):
+    """BASELINE configs[3] as SURVEY §8(d) defines it: every cloth of the ensemble has its own mouse.  clothgpu_step_each on
+    the packed wavefront path: the entry warps use the frame of the cloth a row belongs to, the sweeps learn per stick
+    whether its cloth is being dragged (block state bits 12..15).  Neighbouring cloths in the band (side by side and
+    stacked) get different buttons on purpose: a drag next to an idle cloth next to a hole punch."""
+    desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, ensemble=E, max_iterations=K)
+    g = clothgpu.Cloth(desc)
+    g.set_schedule(SCHED_WAVE)
+    one = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=K)
+    oracles = [oracle.OracleCloth(one, oracle.COLOUR) for _ in range(E)]
+    for e in range(E):
+        st = random_state(nx, ny, seed=2000 + 13 * e + ny)
+        g.write_state(*st, cloth=e)
+        oracles[e].write_state(*st)
+
+    def frames_at(t):
+        out = []
+        for e in range(E):
+            f = _abi.default_frame(K)
+            f.win_w, f.win_h = 128 + 6 * nx + 50, 164 + 6 * ny + 20
+            f.tear_length = 9.5
+            f.mouse_x, f.mouse_y = 128.0 + 6 * nx * ((e * 37 + t * 11) % 17) / 16.0, 164.0 + 6 * ny * ((e * 5 + t * 3) % 7) / 6.0
+            f.mouse_px, f.mouse_py = f.mouse_x - 8.0 - e, f.mouse_y + 5.0
+            kind = (e + t) % 4
+            if kind == 0:
+                f.buttons = _abi.MOUSE_LEFT | MOUSE_DRAGGING
+                f.mouse_force = 1.0 + e
+            elif kind == 1:
+                f.buttons = _abi.MOUSE_RIGHT
+                f.scroll_y = 35.0 + e
+            elif kind == 2:
+                f.buttons = _abi.MOUSE_LEFT | _abi.MOUSE_CTRL
+            f.slider[1] = 200.0 + 10 * e          # gravity differs per cloth too
+            out.append(f)
+        return out
+
+    torn = 0
+    for t in range(4):
+        fr = frames_at(t)
+        g.step_each(fr)
+        for e in range(E):
+            oracles[e].step(fr[e])
+            torn += oracles[e].torn_last
+    assert g.last_schedule()[1] == "wave_frame_kernel<double,PER_CLOTH,PACK>"
+    relax = 0
+    for e in range(E):
+        assert_same_state(g.read_state(cloth=e), oracles[e].read_state(), f"{nx}x{ny} K={K} cloth {e} of {E}, per-cloth frames")
+        relax += oracles[e].relaxations
+    assert torn > 0, "dragged cloths tear, the others must not"
+    c = g.counters()
+    assert c["relaxations"] == relax
+    bad = frames_at(0)
+    bad[1].relax_gain = 0.3
+    with pytest.raises(clothgpu.ClothGpuError):
+        g.step_each(bad)
