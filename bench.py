@@ -596,6 +596,16 @@ def sub_workload(ctx, name, steps, warmup):
         out["fp64_pipe"] = {"frac": (m["value"] / arm.world) * FP64_INSTR_PER_RELAX / FP64_PIPE_PEAK,
                             "what": f"relaxations/s per GPU x {FP64_INSTR_PER_RELAX:.0f} binary64 instructions per stretched stick / {FP64_PIPE_PEAK:.1e} "
                                     f"thread-instructions/s (tools/pipe_peaks.cu): the first roof for K >= 3, shown beside the HBM fraction"}
+    if name == "c0":
+        # the same trace as ONE launch of the resident CTA (CLOTHGPU_SCHED_RESIDENT, csrc/cloth_small.cuh)
+        arm.cloth.set_schedule(arm.abi.SCHED_RESIDENT)
+        ms_res = []
+        for _ in range(5):
+            arm.cloth.reset(128, 164)
+            arm.cloth.sync()
+            ms_res.append(ctx.timed(lambda: arm.issue(0, 1000)))
+        arm.cloth.set_schedule(arm.abi.SCHED_AUTO)
+        out["resident_single_launch_ms_per_step"] = sorted(ms_res)[2] / 1000
     if name in ("c0", "c2t"):
         if name == "c0":
             arm.cloth.reset(128, 164)
@@ -604,6 +614,7 @@ def sub_workload(ctx, name, steps, warmup):
         cpu = cpu_run("c0", steps=1000, warmup=0)
         out["cpu"] = {k: cpu[k] for k in ("value", "frames_per_s", "ms_per_frame", "cores", "kind", "sample")}
         out["side_by_side_ms_per_frame"] = {"cpu_port_physics_only": cpu["ms_per_frame"], "gpu_device": m["ms_per_step"],
+                                            "gpu_device_resident_single_launch": out["resident_single_launch_ms_per_step"],
                                             "gpu_e2e_render": out["e2e_render"]["ms_per_frame"]}
     arm.close()
     return out

@@ -289,8 +289,11 @@ __device__ __forceinline__ void segment_quad(const float4 s, float line_width, f
 // buffer at their rank, then copied out as ONE contiguous, fully coalesced run (before ranking the sticks of consecutive
 // lanes are not adjacent in the output: a lane has 0, 1 or 2 of them).  QUADS: the run is written as outline quads
 // (2 float4 per stick, addSegment) instead of endpoint pairs.
+#ifndef SEG_MIN_BLOCKS
+#define SEG_MIN_BLOCKS 4
+#endif
 template <typename T, bool QUADS>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, SEG_MIN_BLOCKS)
     segment_export_kernel(Planes<T> P, Geom g, int cloth, unsigned long long* __restrict__ status, unsigned long long* ticket,
                           unsigned long long ticket_base, unsigned int epoch, unsigned int n_blocks, float line_width,
                           float4* __restrict__ out, uint8_t* __restrict__ hl, uint2* __restrict__ idx,

@@ -43,36 +43,6 @@ struct Stream1Plan {
     long long tasks; // windows * chunks * ensemble
 };
 
-// Asynchronous global -> shared copy of one lane's 16 (8 in F32) bytes; pred == false zero-fills instead of reading.
-#ifndef S1_STCS
-#define S1_STCS 0
-#endif
-#ifndef S1_LDHINT
-#define S1_LDHINT 0
-#endif
-template <int BYTES>
-__device__ __forceinline__ void cp_async_lane(void* smem, const void* gmem, bool pred) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int n = pred ? BYTES : 0;
-#if S1_LDHINT
-    if (BYTES == 16) {
-        unsigned long long pol;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(s), "l"(gmem), "r"(n), "l"(pol) : "memory");
-        return;
-    }
-#endif
-    if (BYTES == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <typename T>
 struct RowRaw {  // one row of a lane's column pair, as loaded
     typename Vec2<T>::type x, y, px, py;
@@ -280,6 +250,10 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         }
         const bool own_r[2] = {r >= ra && r < rb, r + 1 >= ra && r + 1 < rb};
         bool touched = false;
+#if defined(S1_NO_MATH)  // timing experiment only: what the memory system gives this access pattern without the sticks
+        if (u.iterations == 12345)
+#endif
+        {
         {  // ---- H-even: the lane's own pair, rows r and r+1
             V2* hh[2] = {&E[0], &E[1]};
             V2* tt[2] = {&O[0], &O[1]};
@@ -342,6 +316,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
             if (own_cols && r - 1 >= ra && r - 1 < rb) visits += __popc(live), torn += __popc(tore);
             if (DRAG && (tore & 1u)) cfe &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
             if (DRAG && (tore & 2u)) cfo &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+        }
         }
         store_xy(r - 1, cE, cO, cfe, cfo);  // both rows have now seen all four colours
         store_xy(r, E[0], O[0], fe[0], fo[0]);

@@ -196,6 +196,38 @@ struct StripSync {
     }
 };
 
+// Asynchronous global -> shared copy of one lane's 16, 8 or 4 bytes; pred == false zero-fills instead of reading.
+#ifndef S1_STCS
+#define S1_STCS 0
+#endif
+#ifndef S1_LDHINT
+#define S1_LDHINT 0
+#endif
+template <int BYTES>
+__device__ __forceinline__ void cp_async_lane(void* smem, const void* gmem, bool pred) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = pred ? BYTES : 0;
+#if S1_LDHINT
+    if (BYTES == 16) {
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(s), "l"(gmem), "r"(n), "l"(pol) : "memory");
+        return;
+    }
+#endif
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+    else if (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // (*particle).update, physics/particle.go:75-181.  `fl` is the particle's flag byte.
 template <typename T>
 __device__ __forceinline__ void particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,

@@ -17,6 +17,7 @@
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
 #include "cloth_selftest.cuh"
+#include "cloth_small.cuh"
 #include "cloth_stream1.cuh"
 #include "cloth_wave.cuh"
 #include "frame_fold.h"
@@ -100,6 +101,9 @@ struct clothgpu {
     int s1_chunk_rows = 0;   // 0: chosen per launch
     int wave_chunk_rows = 0; // 0: chosen per launch
     int wave_auto = 1;       // AUTO may pick the wavefront kernel
+    // AUTO does NOT take the resident kernel by itself: measured on the default 171 x 36 cloth it needs 14.3 us per frame
+    // (one SM's binary64 pipe: ~4 us of arithmetic per frame at best) against 8.2 us for one multi-CTA launch per frame.
+    int small_auto = 0;
     int wave_pack = 1;       // ensembles of narrow cloths run on the wavefront kernel as one tall virtual cloth
     int s1_ring = 2;         // shared-memory prefetch ring depth of stream1_frame_kernel (0: register prefetch)
     int s1_warps_per_sm = 4 * S1_RING_CTAS;  // resident warps of stream1_frame_kernel per SM (its launch bounds)
@@ -124,6 +128,9 @@ struct clothgpu {
     } link[2];                       // 0 = upper neighbour, 1 = lower neighbour
     unsigned int epoch = 0;          // operations (fused launches, pushes) done since attach
     // scratch for segment export
+    void* small_frames_dev = nullptr;   // folded FrameU per frame of a resident multi-frame launch (cloth_small.cuh)
+    void* small_frames_host = nullptr;  // pinned staging for the above
+    size_t small_frames_cap = 0;
     unsigned long long* seg_status = nullptr;  // look-back status word per block of the export kernel (never cleared: epoch-tagged)
     size_t seg_status_cap = 0;
     void* seg_out = nullptr;                   // per possible stick: 32 B (quads, or endpoints + indices) + 1 highlight byte
@@ -557,6 +564,63 @@ int launch_streaming(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth
 // before the frame's first launch.
 namespace {
 
+// A cloth small enough to live in the shared memory of one CTA (cloth_small.cuh): one cloth, not a strip.
+bool small_ok(const clothgpu* c) {
+    const Geom& g = c->g;
+    const long long n = (long long)g.nx * g.own_rows;
+    const size_t bytes = c->precision == CLOTHGPU_F32 ? small_smem_bytes<float>(n) : small_smem_bytes<double>(n);
+    return g.ensemble == 1 && c->desc.strip_rows <= 0 && n >= 1 && bytes + 1024 <= (size_t)227 * 1024;
+}
+
+int validate_frame(const clothgpu_frame& f, int i) {
+    const double vals[] = {f.slider[0], f.slider[1], f.slider[2], f.slider[3], f.slider[4], f.drag_force_max,
+                           f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py, f.mouse_force, f.scroll_y,
+                           f.win_off_x, f.win_off_y, f.dt, f.tear_length, f.relax_gain};
+    for (double v : vals)
+        if (!(std::fabs(v) <= kMaxMagnitude))
+            return fail(CLOTHGPU_ERR_INVALID, "frame %d holds a non-finite or absurd value (%g)", i, v);
+    return CLOTHGPU_OK;
+}
+
+// n frames in ONE launch of one resident CTA.
+template <typename T>
+int launch_small(clothgpu* c, const clothgpu_frame* frames, int n) {
+    if (n <= 0) return CLOTHGPU_OK;
+    for (int i = 0; i < n; ++i)
+        if (int rc = validate_frame(frames[i], i)) return rc;
+    if (c->small_frames_cap < (size_t)n) {
+        CU_TRY(cudaStreamSynchronize(c->stream));  // an earlier launch may still read the old buffers
+        cudaFree(c->small_frames_dev);
+        cudaFreeHost(c->small_frames_host);
+        c->small_frames_dev = c->small_frames_host = nullptr;
+        c->small_frames_cap = 0;
+        const size_t cap = std::max<size_t>(64, (size_t)n);
+        CU_TRY(cudaMalloc(&c->small_frames_dev, cap * sizeof(FrameU<double>)));
+        CU_TRY(cudaMallocHost(&c->small_frames_host, cap * sizeof(FrameU<double>)));
+        c->small_frames_cap = cap;
+    }
+    CU_TRY(cudaEventSynchronize(c->frames_copied));  // the previous upload has left the pinned staging buffer
+    FrameU<T>* st = (FrameU<T>*)c->small_frames_host;
+    for (int i = 0; i < n; ++i) st[i] = fold_frame<T>(frames[i], c->desc.spacing);
+    CU_TRY(cudaMemcpyAsync(c->small_frames_dev, st, sizeof(FrameU<T>) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaEventRecord(c->frames_copied, c->stream));
+    const long long np = (long long)c->g.nx * c->g.own_rows;
+    const size_t smem = small_smem_bytes<T>(np);
+    CU_TRY(cudaFuncSetAttribute(small_frames_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    // frame i of the call uses counter slot (ctr_slot + i) & 1; the kernel reports through the slot of the last one
+    DevCounters* last = c->ctr_base + ((c->ctr_slot + n - 1) & 1);
+    small_frames_kernel<T><<<1, kSmallThreads, smem, c->stream>>>(planes<T>(c, c->cur_pos, c->cur_prev), c->g,
+                                                                  (const FrameU<T>*)c->small_frames_dev, n, last);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    c->ctr = last;
+    c->ctr_slot = (c->ctr_slot + n) & 1;
+    c->frames += (uint64_t)n;
+    c->last_sched = CLOTHGPU_SCHED_RESIDENT;
+    c->last_kernel = std::is_same<T, double>::value ? "small_frames_kernel<double>" : "small_frames_kernel<float>";
+    return CLOTHGPU_OK;
+}
+
 template <typename T>
 int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_cloth) {
     // validate first.  Every frame value must be finite and of sane magnitude: with finite inputs the update can
@@ -564,12 +628,7 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     // (cloth_fused.cuh), so the kernels carry no per-stick range test.  (The Go code would propagate NaN instead.)
     for (int i = 0; i < count; ++i) {
         const clothgpu_frame& f = frames[i];
-        const double vals[] = {f.slider[0], f.slider[1], f.slider[2], f.slider[3], f.slider[4], f.drag_force_max,
-                               f.mouse_x, f.mouse_y, f.mouse_px, f.mouse_py, f.mouse_force, f.scroll_y,
-                               f.win_off_x, f.win_off_y, f.dt, f.tear_length, f.relax_gain};
-        for (double v : vals)
-            if (!(std::fabs(v) <= kMaxMagnitude))
-                return fail(CLOTHGPU_ERR_INVALID, "frame %d holds a non-finite or absurd value (%g)", i, v);
+        if (int rc = validate_frame(f, i)) return rc;
         const int K = f.iterations < 1 ? 1 : f.iterations;
         // attached strips refresh their ghost rows after every launch, detached ones once per frame (by the caller)
         const int depth = 2 * (attached(c) ? std::min(K, c->sweeps_per_launch) : K);
@@ -595,6 +654,10 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
     // (cloth_types.cuh, prepare_next_frame_counters): no memset node between two frame kernels
     c->ctr = c->ctr_base + c->ctr_slot;
     int sched = c->schedule;
+    if (sched == CLOTHGPU_SCHED_RESIDENT) {
+        if (!per_cloth && small_ok(c)) return launch_small<T>(c, frames, 1);
+        sched = CLOTHGPU_SCHED_AUTO;  // too large for one CTA's shared memory (or an ensemble): what AUTO would take
+    }
     if (sched == CLOTHGPU_SCHED_AUTO) {
         // One sweep: the row-streaming kernel, unless the cloth is too small to feed enough independent warps.
         // 4..8 sweeps on cloths that fill the 256-column bands and amortise the pipeline ramp: the wavefront kernel
@@ -680,6 +743,8 @@ void free_all(clothgpu* c) {
     cudaFreeHost(c->ctr_host);
     cudaFree(c->frames_dev);
     cudaFreeHost(c->frames_host);
+    cudaFree(c->small_frames_dev);
+    cudaFreeHost(c->small_frames_host);
     cudaFree(c->seg_status);
     cudaFree(c->seg_out);
     cudaFree(c->seg_total);
@@ -808,6 +873,7 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
     if (const char* s = getenv("CLOTHGPU_WAVE_ROWS")) c->wave_chunk_rows = atoi(s) & ~1;
     if (const char* s = getenv("CLOTHGPU_WAVE_AUTO")) c->wave_auto = atoi(s);
     if (const char* s = getenv("CLOTHGPU_WAVE_PACK")) c->wave_pack = atoi(s);
+    if (const char* s = getenv("CLOTHGPU_SMALL_AUTO")) c->small_auto = atoi(s);
     if (const char* s = getenv("CLOTHGPU_S1_RING")) {
         c->s1_ring = atoi(s);
         c->s1_warps_per_sm = c->s1_ring == 2 ? 4 * S1_RING_CTAS : 4 * S1_MIN_CTAS;  // (3 stages: 48 KB per CTA, 4 CTAs fit)
@@ -924,7 +990,11 @@ int clothgpu_step_n(clothgpu* c, const clothgpu_frame* frames, int32_t n) {
     if (!frames || n < 0) return fail(CLOTHGPU_ERR_INVALID, "bad frames/n");
     CU_TRY(cudaEventRecord(c->ev0, c->stream));
     int rc = CLOTHGPU_OK;
-    for (int i = 0; i < n && rc == CLOTHGPU_OK; ++i) rc = step_dispatch(c, frames + i, 1, false);
+    // GUI-sized cloths: all n frames in ONE launch of a resident CTA (cloth_small.cuh) instead of a host loop of launches
+    if (small_ok(c) && ((c->schedule == CLOTHGPU_SCHED_AUTO && n >= 2 && c->small_auto) || c->schedule == CLOTHGPU_SCHED_RESIDENT))
+        rc = c->precision == CLOTHGPU_F32 ? launch_small<float>(c, frames, n) : launch_small<double>(c, frames, n);
+    else
+        for (int i = 0; i < n && rc == CLOTHGPU_OK; ++i) rc = step_dispatch(c, frames + i, 1, false);
     CU_TRY(cudaEventRecord(c->ev1, c->stream));
     c->timed = true;
     return rc;
@@ -967,7 +1037,7 @@ int clothgpu_get_info(clothgpu* c, clothgpu_info* info) {
 
 int clothgpu_set_schedule(clothgpu* c, int32_t schedule) {
     if (!c) return fail(CLOTHGPU_ERR_INVALID, "null handle");
-    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_WAVE)
+    if (schedule < CLOTHGPU_SCHED_AUTO || schedule > CLOTHGPU_SCHED_RESIDENT)
         return fail(CLOTHGPU_ERR_INVALID, "unknown schedule %d", schedule);
     c->schedule = schedule;
     return CLOTHGPU_OK;

@@ -11,7 +11,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NODEVICE, ERR_NOMEM, ERR_STATE, ERR_CAPACITY = 0,
 
 PIN_REFERENCE, PIN_TOP_ROW, PIN_NONE = 0, 1, 2
 F64, F32 = 0, 1
-SCHED_AUTO, SCHED_STREAMING, SCHED_FUSED, SCHED_ROWSTREAM, SCHED_WAVE = 0, 1, 2, 3, 4
+SCHED_AUTO, SCHED_STREAMING, SCHED_FUSED, SCHED_ROWSTREAM, SCHED_WAVE, SCHED_RESIDENT = 0, 1, 2, 3, 4, 5
 
 FLAG_PIN, FLAG_ACTIVE, FLAG_HIGHLIGHT, FLAG_ALIVE_H, FLAG_ALIVE_V = 1, 2, 4, 8, 16
 

@@ -66,8 +66,13 @@ typedef enum clothgpu_schedule {
     CLOTHGPU_SCHED_FUSED = 2,     /* one launch per frame: shared-memory tiles with 2*K halos        */
     CLOTHGPU_SCHED_ROWSTREAM = 3, /* one launch per frame, iterations == 1 only: every warp streams a 64-column window
                                      down the rows in registers (frames with more sweeps fall back to FUSED) */
-    CLOTHGPU_SCHED_WAVE = 4       /* one launch per frame, 2 <= iterations <= 8: rows stream through a shared-memory ring,
+    CLOTHGPU_SCHED_WAVE = 4,      /* one launch per frame, 2 <= iterations <= 8: rows stream through a shared-memory ring,
                                      the sweeps pipelined along the rows (other sweep counts fall back to FUSED) */
+    CLOTHGPU_SCHED_RESIDENT = 5   /* GUI-sized cloths (one cloth of up to ~7000 particles in binary64): ONE resident CTA keeps
+                                     the whole cloth in shared memory and steps all n frames of a clothgpu_step_n call in ONE
+                                     launch (no launch latency between frames, but one SM's arithmetic: measured 14 us per
+                                     frame on the default cloth against 8 us for a multi-CTA launch per frame, so AUTO does not
+                                     pick it).  Larger cloths and ensembles fall back to AUTO. */
 } clothgpu_schedule;
 
 /* Bits of the per-particle flag byte (also the layout returned by clothgpu_read_flags). */
@@ -190,7 +195,8 @@ CLOTHGPU_API void clothgpu_destroy(clothgpu* c);
  * constraint.go:25-64.  Asynchronous on the handle's stream. */
 CLOTHGPU_API int clothgpu_step(clothgpu* c, const clothgpu_frame* frame);
 
-/* n consecutive frames (headless loop); frames[i] is frame i. */
+/* n consecutive frames (headless loop); frames[i] is frame i: one frame-kernel launch per frame, or — on request, for
+ * cloths that fit the shared memory of one SM — all n frames in a single launch (CLOTHGPU_SCHED_RESIDENT). */
 CLOTHGPU_API int clothgpu_step_n(clothgpu* c, const clothgpu_frame* frames, int32_t n);
 
 /* Ensemble handles only: frames[e] drives cloth e (e < ensemble) for one frame.  The frames may differ in everything the
