@@ -70,3 +70,29 @@ def test_snapshot_of_an_ensemble_and_rejections(tmp_path):
     assert h.counters()["frames"] == 7
     x, y, px, py, fl = h.read_state(cloth=2)
     assert np.array_equal(x, states[2][0]) and np.array_equal(py, states[2][3])
+
+
+def test_export_respects_the_callers_capacity():
+    """clothgpu_read_quads_f32 / read_segments_f32 copy small exports back speculatively (count and data in one
+    synchronisation): never beyond the caller's capacity, and a too small capacity is an error, not an overrun."""
+    import ctypes as C
+    g = clothgpu.Cloth(_abi.default_desc())
+    for f in c0_trace(120):
+        g.step(f)
+    quads, hl = g.read_quads()
+    n = len(quads)
+    assert n == g.counters()["live_sticks"] > 12000
+    guard = 64
+    for cap, ok in ((n, True), (n + 3, True), (n - 5, False), (0, False)):
+        qbuf = np.full((cap + guard) * 8, np.float32(-7.0), np.float32)
+        hbuf = np.full(cap + guard, 0xAB, np.uint8)
+        if ok:
+            got = g.read_quads_into(qbuf.ctypes.data, hbuf.ctypes.data, cap)
+            assert got == n
+            assert np.array_equal(qbuf[:n * 8].reshape(-1, 8), quads) and np.array_equal(hbuf[:n], hl)
+        else:
+            with pytest.raises(clothgpu.ClothGpuError) as e:
+                g.read_quads_into(qbuf.ctypes.data, hbuf.ctypes.data, cap)
+            assert e.value.code == _abi.ERR_CAPACITY
+        assert np.all(qbuf[cap * 8:] == np.float32(-7.0)) and np.all(hbuf[cap:] == 0xAB), "wrote past the caller's capacity"
+    assert g.count_segments() == n

@@ -17,6 +17,9 @@ if len(sys.argv) > 5:
     cloth.set_schedule(getattr(_abi, "SCHED_" + sys.argv[5].upper()))
 f = _abi.default_frame(K)
 f.win_w, f.win_h = 128 + 6 * nx + 128, 164 + 6 * ny * 4
+if os.environ.get("CLOTH_DRAG"):      # the DRAG instantiation with the mouse far away: nothing tears, the tear test runs
+    f.buttons = _abi.MOUSE_LEFT | _abi.MOUSE_DRAGGING
+    f.mouse_x = f.mouse_y = f.mouse_px = f.mouse_py = -1.0e6
 stream = torch.cuda.Stream()
 cloth.set_stream(stream.cuda_stream)
 arr = clothgpu.frame_array([f] * frames)
