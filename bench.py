@@ -58,7 +58,7 @@ WORKLOADS = {
     "c3u": (128, 128, 8, 2048, "top_row", "idle", "2048 independent 128x128 cloths per GPU, 8 sweeps/frame, one idle frame for all"),
 }
 # what the default run reports besides the headline (name -> which ranks take part)
-SUBS = ("c4", "c1", "c2t", "c3", "c0")
+SUBS = ("c4", "c4t@f32", "c1", "c2t", "c3", "c0")     # "@f32": the optional binary32 mode of the same workload
 
 
 def peaks():
@@ -561,9 +561,12 @@ def strip_parity(ctx):
 def sub_workload(ctx, name, steps, warmup):
     """One entry of the `workloads` object: value / ms_per_step / roofline.frac / kernel (+ what is specific to it).
     In a multi-rank run only the workloads that shard (strips, ensembles) are run, on every rank."""
+    name, _, prec = name.partition("@")
+    prec = prec or "f64"
     nx, ny, K, cloths, pin, trace, desc_txt = WORKLOADS[name]
-    arm = Arm(ctx, name)
-    out = {"workload": desc_txt, "n_gpus": arm.world}
+    arm = Arm(ctx, name, precision=prec)
+    out = {"workload": desc_txt + (" [optional binary32 mode: state and arithmetic in f32]" if prec == "f32" else ""), "n_gpus": arm.world,
+           "dtype": prec}
     if name == "c0":
         # the whole 1000-frame scripted trace from the rest state per block; Reset (cloth.go:142-148) between blocks
         blocks = []
@@ -586,9 +589,13 @@ def sub_workload(ctx, name, steps, warmup):
     kernel = arm.cloth.last_schedule()[1]
     kms = frame_kernel_time(ctx, arm, steps, used) if arm.compact else m["ms_per_step"]
     launches_per_frame = max(1, -(-K // 8)) if kernel.startswith("fused") else 1
-    rf = roofline_of(arm, kms / launches_per_frame, kernel, name)
+    rf = roofline_of(arm, kms / launches_per_frame, kernel, name if prec == "f64" else None)
     out["kernel"] = kernel
     out["roofline"] = {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_is", "algorithmic_bytes_per_launch")}
+    if prec == "f32":
+        out["note"] = ("binary32 mode: same kernel with 8-byte column pairs per lane and the plain IEEE sqrt / division of binary32 — as many "
+                       "instructions per particle as binary64 for half the bytes, so it is bound by issue slots, not by HBM (33.1 B/particle); "
+                       "it exists for parity with a binary32 oracle, a throughput version needs four columns per lane")
     if arm.compact:
         out["frame_kernel_ms"] = kms
         out["compaction_ms"] = m["ms_per_step"] - kms
@@ -701,7 +708,7 @@ def main():
     if wl == "c4t" and not args.no_subs:
         subs = {}
         for name in [s for s in args.subs.split(",") if s]:
-            if ctx.world > 1 and name not in ("c4", "c3"):
+            if ctx.world > 1 and name not in ("c4", "c3", "c4t@f32"):
                 continue        # single-GPU configurations are reported by the N = 1 run
             subs[name] = sub_workload(ctx, name, args.steps, args.warmup)
         line["workloads"] = subs
