@@ -1,25 +1,28 @@
 // cloth_stream1.cuh — the reference's own frame (ONE relaxation sweep, physics/cloth.go:96-100) as a single streaming
-// pass over HBM: no shared memory, no block barriers, every warp independent.
+// pass over HBM: no block barriers, every warp independent.
 //
 // With one sweep per frame the launch is bound by HBM, not by arithmetic, so the job is to keep loads in flight.
-// A warp owns a window of 64 columns (one (even, odd) column pair per lane, 128-bit accesses, 512 contiguous bytes per
-// warp and plane) and marches down a chunk of rows two at a time, holding a sliding window of three rows in registers:
+// A lane owns NP (even, odd) column pairs of every plane row — one pair: 16 bytes in binary64, 8 in binary32; the code is
+// written for any NP — so a warp owns a window of 64 NP columns, contiguous per warp and plane, and marches down a chunk
+// of rows two at a time, holding a sliding window of three rows in registers:
 //
 //     load rows (r, r+1)  ->  particle_update (cloth.go:92-94; previous positions go straight back to HBM)
-//       H-even   the lane's own pair                                    in registers
-//       H-odd    odd column of lane i  <->  even column of lane i+1     two warp shuffles each way
-//       V-even   rows (r, r+1)                                          in registers
-//       V-odd    rows (r-1, r), r-1 carried from the previous trip      in registers
+//       H-even   the lane's own pair(s)                                          in registers
+//       H-odd    odd column of a pair  <->  even column of the next pair         in registers inside the lane,
+//                                                                                two warp shuffles each way across lanes
+//       V-even   rows (r, r+1)                                                   in registers
+//       V-odd    rows (r-1, r), r-1 carried from the previous trip               in registers
 //     store rows (r-1, r), carry row r+1
 //
 // so every particle is read once and written once.  The colour order H-even, H-odd, V-even, V-odd of the whole-cloth
 // pass is respected because each stick only needs its two endpoints to have finished the previous colours, which the
 // row pipeline guarantees (V-even of a pair after both H passes of both rows, V-odd after the V-even of both pairs it
-// joins).  Column halo: lane 0's even column misses its H-odd stick to the left and lane 31's odd column the one to
-// the right, so windows advance by 60 columns and lanes 0 / 31 are recomputed by the neighbouring warp (except at the
-// cloth's edge, where those sticks do not exist).  Row halo: a chunk reads two rows above and below its owned rows.
-// Loads run two trips ahead of the arithmetic: every lane owns a small ring of shared-memory slots that cp.async fills
-// (a lane only reads back what it copied itself, so this needs no barrier and no registers for the data in flight).
+// joins).  Column halo: lane 0's first column misses its H-odd stick to the left and lane 31's last column the one to
+// the right, so windows advance by 30 lanes' worth of columns and lanes 0 / 31 are recomputed by the neighbouring warp
+// (except at the cloth's edge, where those sticks do not exist).  Row halo: a chunk reads two rows above and below its
+// owned rows.  Loads run two trips ahead of the arithmetic: every lane owns a small ring of shared-memory slots that
+// cp.async fills (a lane only reads back what it copied itself, so this needs no barrier and no registers for the data in
+// flight).
 #pragma once
 #include "cloth_fused.cuh"
 #include "cloth_kernels.cuh"
@@ -34,7 +37,45 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
-constexpr int kS1WindowStep = 60;     // columns a window advances by (30 owned pairs + 1 halo pair per side)
+
+// What a lane owns of one plane row: 16 bytes = NP (even, odd) column pairs.
+template <typename T>
+struct S1Lane;
+template <>
+struct S1Lane<double> {
+    using vec = double2;
+    static constexpr int NP = 1;
+    static __device__ __forceinline__ double get(const vec& v, int i) { return i == 0 ? v.x : v.y; }
+    static __device__ __forceinline__ void set(vec& v, int i, double a) { (i == 0 ? v.x : v.y) = a; }
+    static __device__ __forceinline__ uint32_t load_flags(const uint8_t* p) { return *reinterpret_cast<const unsigned short*>(p); }
+    static __device__ __forceinline__ void store_flags(uint8_t* p, uint32_t f) { *reinterpret_cast<unsigned short*>(p) = (unsigned short)f; }
+};
+// binary32: also ONE pair per lane (8 bytes).  Two pairs per lane (float4, `NP = 2`, which the kernel below supports) were
+// measured SLOWER — 4.80 vs 3.77 ms per frame on 16384^2: the binary32 path is bound by the instruction count of the
+// IEEE sqrt / division sequences, not by bytes, and four sticks in flight per pass spill.
+template <>
+struct S1Lane<float> {
+#ifdef S1_F32_TWO_PAIRS
+    using vec = float4;
+    static constexpr int NP = 2;
+    static __device__ __forceinline__ float get(const vec& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+    static __device__ __forceinline__ void set(vec& v, int i, float a) { (i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w) = a; }
+    static __device__ __forceinline__ uint32_t load_flags(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+    static __device__ __forceinline__ void store_flags(uint8_t* p, uint32_t f) { *reinterpret_cast<uint32_t*>(p) = f; }
+#else
+    using vec = float2;
+    static constexpr int NP = 1;
+    static __device__ __forceinline__ float get(const vec& v, int i) { return i == 0 ? v.x : v.y; }
+    static __device__ __forceinline__ void set(vec& v, int i, float a) { (i == 0 ? v.x : v.y) = a; }
+    static __device__ __forceinline__ uint32_t load_flags(const uint8_t* p) { return *reinterpret_cast<const unsigned short*>(p); }
+    static __device__ __forceinline__ void store_flags(uint8_t* p, uint32_t f) { *reinterpret_cast<unsigned short*>(p) = (unsigned short)f; }
+#endif
+};
+template <typename T>
+__host__ __device__ constexpr int s1_window_cols() { return 64 * S1Lane<T>::NP; }   // columns a warp loads
+template <typename T>
+__host__ __device__ constexpr int s1_window_step() { return 60 * S1Lane<T>::NP; }   // columns a window advances by (30 lanes owned + 1 halo lane per side)
+constexpr int kS1WindowStep = 60;     // (binary64; kept for the host's AUTO heuristics)
 
 struct Stream1Plan {
     int windows;     // column windows per cloth
@@ -44,9 +85,9 @@ struct Stream1Plan {
 };
 
 template <typename T>
-struct RowRaw {  // one row of a lane's column pair, as loaded
-    typename Vec2<T>::type x, y, px, py;
-    uint32_t fl;  // low byte = even column, next byte = odd column
+struct RowRaw {  // one row of a lane's columns, as loaded
+    typename S1Lane<T>::vec x, y, px, py;
+    uint32_t fl;  // byte c = column c of the lane
 };
 
 // RING == 0: the next trip's loads wait in registers.  RING >= 2: every lane owns RING slots of 8 x 16 B in shared memory
@@ -57,7 +98,10 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     stream1_frame_kernel(Planes<T> in, Planes<T> out, Geom g, Stream1Plan pl, const FrameU<T> u0,
                          const FrameU<T>* __restrict__ per_cloth, DevCounters* ctr, const PeerOut<T> peer_up,
                          const PeerOut<T> peer_dn, const StripSync ss) {
-    using V2 = typename Vec2<T>::type;
+    using V2 = typename Vec2<T>::type;          // one particle's (x, y)
+    using L = S1Lane<T>;
+    using VL = typename L::vec;                 // 16 bytes of one plane row
+    constexpr int NP = L::NP, NC = 2 * NP;      // column pairs / columns per lane
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     prepare_next_frame_counters(ctr);
@@ -73,11 +117,11 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     const FrameU<T> u = pick_frame<T, PER_CLOTH>(u0, per_cloth, e);
     const bool dragging = DRAG && (u.buttons & CLOTHGPU_MOUSE_DRAGGING) != 0;
 
-    const int c0 = w * kS1WindowStep;
-    const int ce = c0 + 2 * lane;  // my even column; the odd one is ce + 1
-    const bool ex_e = ce < g.nx, ex_o = ce + 1 < g.nx;
-    // pairs whose two columns come out right in this window (see the header): they are stored by this warp
-    const bool own_cols = ex_e && (lane >= 1 || w == 0) && (lane <= 30 || c0 + 64 >= g.nx);
+    const int c0 = w * s1_window_step<T>();
+    const int ce = c0 + NC * lane;  // my first column
+    const bool ex_e = ce < g.nx;    // my columns exist from the left: column ce + c exists iff ce + c < nx
+    // lanes whose columns all come out right in this window (see the header): they are stored by this warp
+    const bool own_cols = ex_e && (lane >= 1 || w == 0) && (lane <= 30 || c0 + s1_window_cols<T>() >= g.nx);
     const int held_end = g.held_row0 + g.held_rows;
     const int own_end = g.own_row0 + g.own_rows;
     const int ra = g.own_row0 + chunk * pl.chunk_rows, rb = min(ra + pl.chunk_rows, own_end);  // owned rows [ra, rb)
@@ -92,66 +136,70 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
 
     auto load_row = [&](int gy) -> RowRaw<T> {
         RowRaw<T> r;
-        r.x.x = r.x.y = r.y.x = r.y.y = r.px.x = r.px.y = r.py.x = r.py.y = T(0);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) L::set(r.x, c, T(0)), L::set(r.y, c, T(0)), L::set(r.px, c, T(0)), L::set(r.py, c, T(0));
         r.fl = 0;
         if (gy < re && ex_e) {
             const long long at = cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce;
-            r.x = *reinterpret_cast<const V2*>(in.x + at);
-            r.y = *reinterpret_cast<const V2*>(in.y + at);
-            r.px = *reinterpret_cast<const V2*>(in.px + at);
-            r.py = *reinterpret_cast<const V2*>(in.py + at);
-            r.fl = *reinterpret_cast<const unsigned short*>(in.fl + at);
-            if (!ex_o) r.fl &= 0xffu;  // column nx (row padding) does not exist
+            r.x = *reinterpret_cast<const VL*>(in.x + at);
+            r.y = *reinterpret_cast<const VL*>(in.y + at);
+            r.px = *reinterpret_cast<const VL*>(in.px + at);
+            r.py = *reinterpret_cast<const VL*>(in.py + at);
+            r.fl = L::load_flags(in.fl + at);
         }
         return r;
     };
-    auto store_xy = [&](int gy, const V2& pe, const V2& po, uint32_t fe, uint32_t fo) {
+    // E[p] / O[p] = the even / odd column of pair p
+    auto store_xy = [&](int gy, const V2 (&pe)[NP], const V2 (&po)[NP], const uint32_t (&fe)[NP], const uint32_t (&fo)[NP]) {
         if (!own_cols || gy < ra || gy >= rb) return;
         const long long at = cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce;
-        V2 ox2, oy2;
-        ox2.x = pe.x, ox2.y = po.x, oy2.x = pe.y, oy2.y = po.y;
-        const unsigned short ff = (unsigned short)((fe & 0xffu) | ((fo & 0xffu) << 8));
+        VL ox2, oy2;
+        uint32_t ff = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            L::set(ox2, 2 * p, pe[p].x), L::set(ox2, 2 * p + 1, po[p].x), L::set(oy2, 2 * p, pe[p].y), L::set(oy2, 2 * p + 1, po[p].y);
+            ff |= ((fe[p] & 0xffu) | ((fo[p] & 0xffu) << 8)) << (16 * p);
+        }
 #if S1_STCS  // streaming stores: the planes are far larger than L2 and are read again only by the NEXT frame
-        __stcs(reinterpret_cast<V2*>(out.x + at), ox2);
-        __stcs(reinterpret_cast<V2*>(out.y + at), oy2);
-        __stcs(reinterpret_cast<unsigned short*>(out.fl + at), (unsigned short)ff);
+        __stcs(reinterpret_cast<VL*>(out.x + at), ox2);
+        __stcs(reinterpret_cast<VL*>(out.y + at), oy2);
 #else
-        *reinterpret_cast<V2*>(out.x + at) = ox2;
-        *reinterpret_cast<V2*>(out.y + at) = oy2;
-        *reinterpret_cast<unsigned short*>(out.fl + at) = ff;
+        *reinterpret_cast<VL*>(out.x + at) = ox2;
+        *reinterpret_cast<VL*>(out.y + at) = oy2;
 #endif
+        L::store_flags(out.fl + at, ff);
         if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {  // the neighbouring strip's ghost copy of this row
             const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + ce;
-            *reinterpret_cast<V2*>(peer_up.x + pat) = ox2;
-            *reinterpret_cast<V2*>(peer_up.y + pat) = oy2;
-            *reinterpret_cast<unsigned short*>(peer_up.fl + pat) = ff;
+            *reinterpret_cast<VL*>(peer_up.x + pat) = ox2;
+            *reinterpret_cast<VL*>(peer_up.y + pat) = oy2;
+            L::store_flags(peer_up.fl + pat, ff);
         }
         if (gy >= peer_dn.row_lo && gy < peer_dn.row_hi) {
             const long long pat = (long long)e * peer_dn.cloth_stride + (long long)(gy - peer_dn.held_row0) * g.pitch + ce;
-            *reinterpret_cast<V2*>(peer_dn.x + pat) = ox2;
-            *reinterpret_cast<V2*>(peer_dn.y + pat) = oy2;
-            *reinterpret_cast<unsigned short*>(peer_dn.fl + pat) = ff;
+            *reinterpret_cast<VL*>(peer_dn.x + pat) = ox2;
+            *reinterpret_cast<VL*>(peer_dn.y + pat) = oy2;
+            L::store_flags(peer_dn.fl + pat, ff);
         }
     };
-    auto store_prev = [&](int gy, const V2& vpx, const V2& vpy) {
+    auto store_prev = [&](int gy, const VL& vpx, const VL& vpy) {
         if (!own_cols || gy < ra || gy >= rb) return;
         const long long at = cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce;
 #if S1_STCS
-        __stcs(reinterpret_cast<V2*>(out.px + at), vpx);
-        __stcs(reinterpret_cast<V2*>(out.py + at), vpy);
+        __stcs(reinterpret_cast<VL*>(out.px + at), vpx);
+        __stcs(reinterpret_cast<VL*>(out.py + at), vpy);
 #else
-        *reinterpret_cast<V2*>(out.px + at) = vpx;
-        *reinterpret_cast<V2*>(out.py + at) = vpy;
+        *reinterpret_cast<VL*>(out.px + at) = vpx;
+        *reinterpret_cast<VL*>(out.py + at) = vpy;
 #endif
         if (gy >= peer_up.row_lo && gy < peer_up.row_hi) {
             const long long pat = (long long)e * peer_up.cloth_stride + (long long)(gy - peer_up.held_row0) * g.pitch + ce;
-            *reinterpret_cast<V2*>(peer_up.px + pat) = vpx;
-            *reinterpret_cast<V2*>(peer_up.py + pat) = vpy;
+            *reinterpret_cast<VL*>(peer_up.px + pat) = vpx;
+            *reinterpret_cast<VL*>(peer_up.py + pat) = vpy;
         }
         if (gy >= peer_dn.row_lo && gy < peer_dn.row_hi) {
             const long long pat = (long long)e * peer_dn.cloth_stride + (long long)(gy - peer_dn.held_row0) * g.pitch + ce;
-            *reinterpret_cast<V2*>(peer_dn.px + pat) = vpx;
-            *reinterpret_cast<V2*>(peer_dn.py + pat) = vpy;
+            *reinterpret_cast<VL*>(peer_dn.px + pat) = vpx;
+            *reinterpret_cast<VL*>(peer_dn.py + pat) = vpy;
         }
     };
     auto live_of = [](uint32_t fh, uint32_t ft, uint32_t alive) -> uint32_t {
@@ -167,15 +215,16 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     unsigned int visits = 0, torn = 0;
     ParticleEvents events;
     // the row carried from the previous trip (global row r - 1): after V-even, waiting for its V-odd stick
-    V2 cE, cO;
-    cE.x = cE.y = cO.x = cO.y = T(0);
-    uint32_t cfe = 0, cfo = 0;
+    V2 cE[NP], cO[NP];
+    uint32_t cfe[NP], cfo[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) cE[p].x = cE[p].y = cO[p].x = cO[p].y = T(0), cfe[p] = cfo[p] = 0;
 
     // ---- prefetch machinery -------------------------------------------------------------------------------------
     extern __shared__ __align__(16) unsigned char s1_smem[];
-    // slot (stage, q, plane) of this lane: 32 lanes x sizeof(V2) contiguous, conflict-free
-    auto slot = [&](int stage, int q, int plane) -> V2* {
-        return reinterpret_cast<V2*>(s1_smem) + ((((threadIdx.x >> 5) * (RING ? RING : 1) + stage) * 8 + q * 4 + plane) * 32 + lane);
+    // slot (stage, q, plane) of this lane: 32 lanes x sizeof(VL) contiguous, conflict-free
+    auto slot = [&](int stage, int q, int plane) -> VL* {
+        return reinterpret_cast<VL*>(s1_smem) + ((((threadIdx.x >> 5) * (RING ? RING : 1) + stage) * 8 + q * 4 + plane) * 32 + lane);
     };
     auto issue_trip = [&](int r, int stage) {  // rows r, r+1 -> stage (RING > 0 only)
 #pragma unroll
@@ -183,21 +232,25 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
             const int gy = r + q;
             const bool ok = gy < re && ex_e;
             const long long at = ok ? cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce : 0;
-            cp_async_lane<sizeof(V2)>(slot(stage, q, 0), in.x + at, ok);
-            cp_async_lane<sizeof(V2)>(slot(stage, q, 1), in.y + at, ok);
-            cp_async_lane<sizeof(V2)>(slot(stage, q, 2), in.px + at, ok);
-            cp_async_lane<sizeof(V2)>(slot(stage, q, 3), in.py + at, ok);
+            cp_async_lane<sizeof(VL)>(slot(stage, q, 0), in.x + at, ok);
+            cp_async_lane<sizeof(VL)>(slot(stage, q, 1), in.y + at, ok);
+            cp_async_lane<sizeof(VL)>(slot(stage, q, 2), in.px + at, ok);
+            cp_async_lane<sizeof(VL)>(slot(stage, q, 3), in.py + at, ok);
         }
         cp_async_commit();
     };
-    // (the value is used RING trips later; nothing may touch it before — masking the non-existent odd column right here
+    // (the value is used RING trips later; nothing may touch it before — masking the non-existent columns right here
     //  made every warp wait for the load at once: 17 % of all stall samples of the launch sat on that one instruction)
     auto load_flags = [&](int gy) -> uint32_t {
         uint32_t f = 0;
-        if (gy < re && ex_e) f = *reinterpret_cast<const unsigned short*>(in.fl + cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce);
+        if (gy < re && ex_e) f = L::load_flags(in.fl + cloth_base + (long long)(gy - g.held_row0) * g.pitch + ce);
         return f;
     };
-    const uint32_t fl_keep = ex_o ? 0xffffu : 0xffu;  // column nx (row padding) does not exist
+    // columns of the row padding (ce + c >= nx) do not exist: their flag bytes are dropped where the flags are used
+    uint32_t fl_keep = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (ce + c < g.nx) fl_keep |= 0xffu << (8 * c);
 
     RowRaw<T> nxt0, nxt1;
     uint32_t fq[RING ? 2 * RING : 1];  // flags of the trips in flight (RING > 0)
@@ -217,6 +270,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         if (RING == 0) {
             // (a ping-pong of two register sets instead of these copies measured slower: twice the code, worse schedule)
             raw0 = nxt0, raw1 = nxt1;
+            raw0.fl &= fl_keep, raw1.fl &= fl_keep;
             nxt0 = load_row(r + 2);  // in flight during this trip's arithmetic (rows >= re load nothing)
             nxt1 = load_row(r + 3);
         } else {
@@ -230,23 +284,29 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
             fq[2 * RING - 2] = load_flags(r + 2 * RING), fq[2 * RING - 1] = load_flags(r + 2 * RING + 1);
             stage = stage + 1 == RING ? 0 : stage + 1;
         }
-        V2 E[2], O[2];
-        uint32_t fe[2], fo[2];
+        V2 E[2][NP], O[2][NP];
+        uint32_t fe[2][NP], fo[2][NP];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {  // ---- loop over particles, cloth.go:92-94
             const RowRaw<T>& rw = q ? raw1 : raw0;
-            E[q].x = rw.x.x, O[q].x = rw.x.y, E[q].y = rw.y.x, O[q].y = rw.y.y;
-            fe[q] = rw.fl & 0xffu, fo[q] = rw.fl >> 8;
-            T px0 = rw.px.x, px1 = rw.px.y, py0 = rw.py.x, py1 = rw.py.y;
-            if (r + q < re && ex_e) {
-                const uint32_t fe_in = fe[q], fo_in = fo[q];
-                particle_update(E[q].x, E[q].y, px0, py0, fe[q], u);
-                if (ex_o) particle_update(O[q].x, O[q].y, px1, py1, fo[q], u);
-                if (own_cols && r + q >= ra && r + q < rb) events.note2(fe_in, fe[q], fo_in, fo[q]);
-                V2 vpx, vpy;
-                vpx.x = px0, vpx.y = px1, vpy.x = py0, vpy.y = py1;
-                store_prev(r + q, vpx, vpy);
+            VL vpx = rw.px, vpy = rw.py;
+            const bool row_ok = r + q < re && ex_e;
+            const bool counted = own_cols && r + q >= ra && r + q < rb;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                E[q][p].x = L::get(rw.x, 2 * p), O[q][p].x = L::get(rw.x, 2 * p + 1);
+                E[q][p].y = L::get(rw.y, 2 * p), O[q][p].y = L::get(rw.y, 2 * p + 1);
+                fe[q][p] = (rw.fl >> (16 * p)) & 0xffu, fo[q][p] = (rw.fl >> (16 * p + 8)) & 0xffu;
+                if (row_ok) {
+                    const uint32_t fe_in = fe[q][p], fo_in = fo[q][p];
+                    T px0 = L::get(vpx, 2 * p), px1 = L::get(vpx, 2 * p + 1), py0 = L::get(vpy, 2 * p), py1 = L::get(vpy, 2 * p + 1);
+                    if (NP == 1 || ce + 2 * p < g.nx) particle_update(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u);
+                    if (ce + 2 * p + 1 < g.nx) particle_update(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u);
+                    L::set(vpx, 2 * p, px0), L::set(vpx, 2 * p + 1, px1), L::set(vpy, 2 * p, py0), L::set(vpy, 2 * p + 1, py1);
+                    if (counted) events.note2(fe_in, fe[q][p], fo_in, fo[q][p]);
+                }
             }
+            if (row_ok) store_prev(r + q, vpx, vpy);
         }
         const bool own_r[2] = {r >= ra && r < rb, r + 1 >= ra && r + 1 < rb};
         bool touched = false;
@@ -254,73 +314,108 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         if (u.iterations == 12345)
 #endif
         {
-        {  // ---- H-even: the lane's own pair, rows r and r+1
-            V2* hh[2] = {&E[0], &E[1]};
-            V2* tt[2] = {&O[0], &O[1]};
+        {  // ---- H-even: the lane's own pairs, rows r and r+1
+            V2* hh[2 * NP];
+            V2* tt[2 * NP];
             uint32_t live = 0, pins = 0;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                live |= live_of(fe[q], fo[q], CLOTHGPU_FLAG_ALIVE_H) << q;
-                pins |= ((fe[q] & CLOTHGPU_FLAG_PIN) | ((fo[q] & CLOTHGPU_FLAG_PIN) << 1)) << (2 * q);
-            }
-            const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, dragging, touched);
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (own_cols && own_r[q]) visits += (live >> q) & 1u, torn += (tore >> q) & 1u;
-                if (DRAG && (tore & (1u << q))) fe[q] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_H;
-            }
+                for (int p = 0; p < NP; ++p) {
+                    const int k = q * NP + p;
+                    hh[k] = &E[q][p], tt[k] = &O[q][p];
+                    live |= live_of(fe[q][p], fo[q][p], CLOTHGPU_FLAG_ALIVE_H) << k;
+                    pins |= ((fe[q][p] & CLOTHGPU_FLAG_PIN) | ((fo[q][p] & CLOTHGPU_FLAG_PIN) << 1)) << (2 * k);
+                }
+            const uint32_t tore = relax_n<T, DRAG, 2 * NP>(hh, tt, live, pins, u, dragging, touched);
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int k = q * NP + p;
+                    if (own_cols && own_r[q]) visits += (live >> k) & 1u, torn += (tore >> k) & 1u;
+                    if (DRAG && (tore & (1u << k))) fe[q][p] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_H;
+                }
         }
-        {  // ---- H-odd: my odd column (head) and the even column of lane + 1 (tail)
+        {  // ---- H-odd: the odd column of a pair (head) and the even column of the next pair (tail): inside the lane for
+           // ---- p < NP - 1, the even column of lane + 1 for the last pair
             V2 Tn[2];
             uint32_t fn[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                Tn[q] = shfl_v2(E[q], true);
-                fn[q] = __shfl_down_sync(FULL, fe[q], 1);
+                Tn[q] = shfl_v2(E[q][0], true);
+                fn[q] = __shfl_down_sync(FULL, fe[q][0], 1);
             }
-            V2* hh[2] = {&O[0], &O[1]};
-            V2* tt[2] = {&Tn[0], &Tn[1]};
+            V2* hh[2 * NP];
+            V2* tt[2 * NP];
             uint32_t live = 0, pins = 0;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (lane < 31) live |= live_of(fo[q], fn[q], CLOTHGPU_FLAG_ALIVE_H) << q;
-                pins |= ((fo[q] & CLOTHGPU_FLAG_PIN) | ((fn[q] & CLOTHGPU_FLAG_PIN) << 1)) << (2 * q);
-            }
-            const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, dragging, touched);
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int k = q * NP + p;
+                    const bool cross = p == NP - 1;
+                    const uint32_t ftail = cross ? fn[q] : fe[q][cross ? 0 : p + 1];
+                    hh[k] = &O[q][p], tt[k] = cross ? &Tn[q] : &E[q][cross ? 0 : p + 1];
+                    if (!cross || lane < 31) live |= live_of(fo[q][p], ftail, CLOTHGPU_FLAG_ALIVE_H) << k;
+                    pins |= ((fo[q][p] & CLOTHGPU_FLAG_PIN) | ((ftail & CLOTHGPU_FLAG_PIN) << 1)) << (2 * k);
+                }
+            const uint32_t tore = relax_n<T, DRAG, 2 * NP>(hh, tt, live, pins, u, dragging, touched);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (own_cols && own_r[q]) visits += (live >> q) & 1u, torn += (tore >> q) & 1u;
-                if (DRAG && (tore & (1u << q))) fo[q] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_H;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int k = q * NP + p;
+                    if (own_cols && own_r[q]) visits += (live >> k) & 1u, torn += (tore >> k) & 1u;
+                    if (DRAG && (tore & (1u << k))) fo[q][p] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_H;
+                }
                 const V2 back = shfl_v2(Tn[q], false);  // the relaxed tail returns to its lane
-                if (lane >= 1) E[q] = back;
+                if (lane >= 1) E[q][0] = back;
             }
         }
-        {  // ---- V-even: rows (r, r+1), both columns
-            V2* hh[2] = {&E[0], &O[0]};
-            V2* tt[2] = {&E[1], &O[1]};
-            const uint32_t live = live_of(fe[0], fe[1], CLOTHGPU_FLAG_ALIVE_V) | (live_of(fo[0], fo[1], CLOTHGPU_FLAG_ALIVE_V) << 1);
-            const uint32_t pins = (fe[0] & CLOTHGPU_FLAG_PIN) | ((fe[1] & CLOTHGPU_FLAG_PIN) << 1) |
-                                  ((fo[0] & CLOTHGPU_FLAG_PIN) << 2) | ((fo[1] & CLOTHGPU_FLAG_PIN) << 3);
-            const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, dragging, touched);
+        {  // ---- V-even: rows (r, r+1), all columns
+            V2* hh[NC];
+            V2* tt[NC];
+            uint32_t live = 0, pins = 0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                hh[2 * p] = &E[0][p], tt[2 * p] = &E[1][p], hh[2 * p + 1] = &O[0][p], tt[2 * p + 1] = &O[1][p];
+                live |= (live_of(fe[0][p], fe[1][p], CLOTHGPU_FLAG_ALIVE_V) | (live_of(fo[0][p], fo[1][p], CLOTHGPU_FLAG_ALIVE_V) << 1)) << (2 * p);
+                pins |= ((fe[0][p] & CLOTHGPU_FLAG_PIN) | ((fe[1][p] & CLOTHGPU_FLAG_PIN) << 1) | ((fo[0][p] & CLOTHGPU_FLAG_PIN) << 2) |
+                         ((fo[1][p] & CLOTHGPU_FLAG_PIN) << 3)) << (4 * p);
+            }
+            const uint32_t tore = relax_n<T, DRAG, NC>(hh, tt, live, pins, u, dragging, touched);
             if (own_cols && own_r[0]) visits += __popc(live), torn += __popc(tore);
-            if (DRAG && (tore & 1u)) fe[0] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
-            if (DRAG && (tore & 2u)) fo[0] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                if (DRAG && (tore & (1u << (2 * p)))) fe[0][p] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+                if (DRAG && (tore & (2u << (2 * p)))) fo[0][p] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+            }
         }
         {  // ---- V-odd: rows (r-1, r); r-1 is the carried row
-            V2* hh[2] = {&cE, &cO};
-            V2* tt[2] = {&E[0], &O[0]};
-            const uint32_t live = live_of(cfe, fe[0], CLOTHGPU_FLAG_ALIVE_V) | (live_of(cfo, fo[0], CLOTHGPU_FLAG_ALIVE_V) << 1);
-            const uint32_t pins = (cfe & CLOTHGPU_FLAG_PIN) | ((fe[0] & CLOTHGPU_FLAG_PIN) << 1) |
-                                  ((cfo & CLOTHGPU_FLAG_PIN) << 2) | ((fo[0] & CLOTHGPU_FLAG_PIN) << 3);
-            const uint32_t tore = relax_n<T, DRAG, 2>(hh, tt, live, pins, u, dragging, touched);
+            V2* hh[NC];
+            V2* tt[NC];
+            uint32_t live = 0, pins = 0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                hh[2 * p] = &cE[p], tt[2 * p] = &E[0][p], hh[2 * p + 1] = &cO[p], tt[2 * p + 1] = &O[0][p];
+                live |= (live_of(cfe[p], fe[0][p], CLOTHGPU_FLAG_ALIVE_V) | (live_of(cfo[p], fo[0][p], CLOTHGPU_FLAG_ALIVE_V) << 1)) << (2 * p);
+                pins |= ((cfe[p] & CLOTHGPU_FLAG_PIN) | ((fe[0][p] & CLOTHGPU_FLAG_PIN) << 1) | ((cfo[p] & CLOTHGPU_FLAG_PIN) << 2) |
+                         ((fo[0][p] & CLOTHGPU_FLAG_PIN) << 3)) << (4 * p);
+            }
+            const uint32_t tore = relax_n<T, DRAG, NC>(hh, tt, live, pins, u, dragging, touched);
             if (own_cols && r - 1 >= ra && r - 1 < rb) visits += __popc(live), torn += __popc(tore);
-            if (DRAG && (tore & 1u)) cfe &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
-            if (DRAG && (tore & 2u)) cfo &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                if (DRAG && (tore & (1u << (2 * p)))) cfe[p] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+                if (DRAG && (tore & (2u << (2 * p)))) cfo[p] &= ~(uint32_t)CLOTHGPU_FLAG_ALIVE_V;
+            }
         }
         }
         store_xy(r - 1, cE, cO, cfe, cfo);  // both rows have now seen all four colours
         store_xy(r, E[0], O[0], fe[0], fo[0]);
-        cE = E[1], cO = O[1], cfe = fe[1], cfo = fo[1];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) cE[p] = E[1][p], cO[p] = O[1][p], cfe[p] = fe[1][p], cfo[p] = fo[1][p];
     }
     // the last carried row has no row below it when the cloth (strip) ends here
     store_xy(rs + ((re - rs + 1) & ~1) - 1, cE, cO, cfe, cfo);

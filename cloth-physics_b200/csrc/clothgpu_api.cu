@@ -369,7 +369,7 @@ template <typename T>
 int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) {
     const Geom& g = c->g;
     Stream1Plan pl{};
-    pl.windows = g.nx <= 64 ? 1 : (g.nx - 64 + kS1WindowStep - 1) / kS1WindowStep + 1;
+    pl.windows = g.nx <= s1_window_cols<T>() ? 1 : (g.nx - s1_window_cols<T>() + s1_window_step<T>() - 1) / s1_window_step<T>() + 1;
     // Row chunks.  Warps are independent and equally loaded, so the launch runs in "waves" of `slots` resident warps
     // (20 per SM with the shared-memory prefetch ring): long chunks amortise the 4 halo rows, but the task count should be just under a
     // whole number of waves.  With many waves the last, partial one no longer matters and 128-row chunks are used.
@@ -417,7 +417,7 @@ int launch_stream1(clothgpu* c, const FrameU<T>& u, const FrameU<T>* per_cloth) 
     };
     auto pick = [&](auto ring) -> cudaError_t {
         constexpr int RING = decltype(ring)::value;
-        const size_t smem = (size_t)RING * kS1Threads * 8 * 2 * sizeof(T);
+        const size_t smem = (size_t)RING * kS1Threads * 8 * 16;  // per lane and stage: 2 rows x 4 planes x 16 bytes
         if (pc) return go(stream1_frame_kernel<T, true, true, RING>, smem);
         return drag ? go(stream1_frame_kernel<T, false, true, RING>, smem) : go(stream1_frame_kernel<T, false, false, RING>, smem);
     };
@@ -663,7 +663,8 @@ int step_frames(clothgpu* c, const clothgpu_frame* frames, int count, bool per_c
         // 4..8 sweeps on cloths that fill the 256-column bands and amortise the pipeline ramp: the wavefront kernel
         // (measured on 4096^2 against the tile kernel: 0.617 vs 0.569 ms at 3 sweeps, 0.683 vs 0.704 at 4, 0.734 vs
         // 0.854 at 5, 0.97 vs 1.48 at 8).
-        const long long warps = (long long)((c->g.nx + kS1WindowStep - 1) / kS1WindowStep) * ((c->g.own_rows + 7) / 8) * c->g.ensemble;
+        const int step = std::is_same<T, float>::value ? s1_window_step<float>() : s1_window_step<double>();
+        const long long warps = (long long)((c->g.nx + step - 1) / step) * ((c->g.own_rows + 7) / 8) * c->g.ensemble;
         if (u0.iterations == 1 && c->k1_stream && warps >= 2ll * c->sm_count)
             sched = CLOTHGPU_SCHED_ROWSTREAM;
         else if (u0.iterations >= 4 && u0.iterations <= kMaxSweepsPerLaunch && c->wave_auto &&

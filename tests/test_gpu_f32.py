@@ -17,6 +17,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("nx,ny,K,schedule", [(171, 36, 1, SCHED_ROWSTREAM), (171, 36, 1, SCHED_FUSED), (130, 131, 3, SCHED_FUSED),
+                                              (700, 219, 1, SCHED_ROWSTREAM), (1037, 90, 1, SCHED_ROWSTREAM), (126, 300, 1, SCHED_ROWSTREAM),
+                                              (3, 40, 1, SCHED_ROWSTREAM), (129, 64, 1, SCHED_ROWSTREAM),
                                               (300, 219, 8, SCHED_WAVE), (129, 33, 2, SCHED_STREAMING)])
 def test_f32_mode_matches_the_binary32_oracle(oracle, nx, ny, K, schedule):
     desc = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=K, precision=_abi.F32)
