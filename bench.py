@@ -593,9 +593,9 @@ def sub_workload(ctx, name, steps, warmup):
     out["kernel"] = kernel
     out["roofline"] = {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_is", "algorithmic_bytes_per_launch")}
     if prec == "f32":
-        out["note"] = ("binary32 mode: same kernel with 8-byte column pairs per lane and the plain IEEE sqrt / division of binary32 — as many "
-                       "instructions per particle as binary64 for half the bytes, so it is bound by issue slots, not by HBM (33.1 B/particle); "
-                       "it exists for parity with a binary32 oracle, a throughput version needs four columns per lane")
+        out["note"] = ("binary32 mode: same kernel, 8-byte column pairs per lane, its own branch-free sqrt / division expansion (proven exact "
+                       "against sqrt.rn.f32 / div.rn.f32 on every operand by clothgpu_selftest_stickmath_f32); as many instructions per "
+                       "particle as binary64 for half the bytes, so it is bound by issue slots rather than by HBM (33.1 B/particle)")
     if arm.compact:
         out["frame_kernel_ms"] = kms
         out["compaction_ms"] = m["ms_per_step"] - kms

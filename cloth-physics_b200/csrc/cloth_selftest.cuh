@@ -85,4 +85,36 @@ __global__ void __launch_bounds__(256) stickmath_list_kernel(const double* __res
     if ((threadIdx.x & 31) == 0 && done) atomicAdd(&rep->tested, done);
 }
 
+// binary32, exhaustive: every s = the float with bit pattern b, b in [bits(1.0f), bits(2^63)), with every rest length
+// 1..64 that leaves the stick stretched.  Grid-stride over b; the 64 rest lengths in the inner loop.
+__global__ void __launch_bounds__(256) stickmath_f32_exhaustive_kernel(float gain, StickMathReport* rep) {
+    constexpr unsigned int b0 = 0x3f800000u, b1 = 0x5f000000u;  // 1.0f, 2^63
+    unsigned long long done = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < (unsigned long long)(b1 - b0);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float s = __uint_as_float(b0 + (unsigned int)i);
+        const float d = __fsqrt_rn(s);
+        for (int Li = 1; Li <= 64; ++Li) {
+            const float L = (float)Li;
+            if (!(s >= L * L)) break;
+            FrameU<float> u{};
+            u.L = L;
+            u.gain = gain;
+            float mul, dist;
+            StickMath<float>::mul_dist(s, u, mul, dist);
+            const float diff = __fdiv_rn(__fsub_rn(L, d), d);
+            const float want = __fmul_rn(__fmul_rn(diff, gain), __fsub_rn(1.0f, __fdiv_rn(L, d)));
+            if (__float_as_uint(d) != __float_as_uint(dist) || __float_as_uint(want) != __float_as_uint(mul)) {
+                if (atomicAdd(&rep->mismatches, 1ull) == 0ull) {
+                    rep->first_s = s, rep->first_L = L;
+                    rep->got_dist = dist, rep->want_dist = d, rep->got_mul = mul, rep->want_mul = want;
+                }
+            }
+            ++done;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) done += __shfl_down_sync(0xffffffffu, done, o);
+    if ((threadIdx.x & 31) == 0 && done) atomicAdd(&rep->tested, done);
+}
+
 }  // namespace clothgpu_impl

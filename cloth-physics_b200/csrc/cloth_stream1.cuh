@@ -50,9 +50,9 @@ struct S1Lane<double> {
     static __device__ __forceinline__ uint32_t load_flags(const uint8_t* p) { return *reinterpret_cast<const unsigned short*>(p); }
     static __device__ __forceinline__ void store_flags(uint8_t* p, uint32_t f) { *reinterpret_cast<unsigned short*>(p) = (unsigned short)f; }
 };
-// binary32: also ONE pair per lane (8 bytes).  Two pairs per lane (float4, `NP = 2`, which the kernel below supports) were
-// measured SLOWER — 4.80 vs 3.77 ms per frame on 16384^2: the binary32 path is bound by the instruction count of the
-// IEEE sqrt / division sequences, not by bytes, and four sticks in flight per pass spill.
+// binary32: also ONE pair per lane (8 bytes).  Two pairs per lane (float4, `-DS1_F32_TWO_PAIRS`, which the kernel below
+// supports) measured 2.43 vs 2.49 ms per frame on 16384^2 with the branch-free binary32 stick arithmetic (and 4.80 vs
+// 3.77 ms with the library's branchy IEEE sequences before it): the binary32 path is bound by issue slots, not by bytes.
 template <>
 struct S1Lane<float> {
 #ifdef S1_F32_TWO_PAIRS

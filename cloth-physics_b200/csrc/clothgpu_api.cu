@@ -1653,6 +1653,33 @@ int clothgpu_selftest_stickmath(int32_t device, uint64_t seed, uint64_t samples,
     return rc;
 }
 
+int clothgpu_selftest_stickmath_f32(int32_t device, clothgpu_stickmath_report* report) {
+    if (!report) return fail(CLOTHGPU_ERR_INVALID, "null report");
+    memset(report, 0, sizeof *report);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CLOTHGPU_ERR_NODEVICE, "no CUDA device (%s); clothgpu has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(CLOTHGPU_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(CLOTHGPU_ERR_NODEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    CU_TRY(cudaSetDevice(device));
+    StickMathReport* d_rep = nullptr;
+    CU_TRY(cudaMalloc((void**)&d_rep, sizeof(StickMathReport)));
+    cudaError_t ee = cudaMemset(d_rep, 0, sizeof(StickMathReport));
+    if (ee == cudaSuccess) {
+        stickmath_f32_exhaustive_kernel<<<prop.multiProcessorCount * 16, 256>>>(0.35f, d_rep);
+        ee = cudaGetLastError();
+    }
+    if (ee == cudaSuccess) ee = cudaDeviceSynchronize();
+    if (ee == cudaSuccess) ee = cudaMemcpy(report, d_rep, sizeof *report, cudaMemcpyDeviceToHost);
+    cudaFree(d_rep);
+    if (ee != cudaSuccess) return fail(CLOTHGPU_ERR_CUDA, "binary32 self-test: %s", cudaGetErrorString(ee));
+    return CLOTHGPU_OK;
+}
+
 const char* clothgpu_last_error(void) { return g_last_error.c_str(); }
 
 const char* clothgpu_version(void) { return "clothgpu 0.1 (sm_100a)"; }

@@ -26,7 +26,7 @@ EXPORTS = [
     "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_read_quads_f32", "clothgpu_compact_segments",
     "clothgpu_get_counters",
     "clothgpu_halo_region", "clothgpu_strip_export", "clothgpu_strip_attach", "clothgpu_strip_push", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
-    "clothgpu_last_schedule", "clothgpu_selftest_stickmath", "clothgpu_save_state", "clothgpu_load_state",
+    "clothgpu_last_schedule", "clothgpu_selftest_stickmath", "clothgpu_selftest_stickmath_f32", "clothgpu_save_state", "clothgpu_load_state",
     "clothgpu_last_error", "clothgpu_version",
 ]
 
@@ -84,6 +84,8 @@ def lib():
             L.clothgpu_last_schedule.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]
             L.clothgpu_selftest_stickmath.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, dp, C.c_size_t,
                                                       C.POINTER(_abi.StickMathReport)]
+        if hasattr(L, "clothgpu_selftest_stickmath_f32"):
+            L.clothgpu_selftest_stickmath_f32.argtypes = [C.c_int32, C.POINTER(_abi.StickMathReport)]
         L.clothgpu_last_error.restype = C.c_char_p
         L.clothgpu_version.restype = C.c_char_p
         _lib = L
@@ -112,6 +114,13 @@ def selftest_stickmath(samples=0, s_list=None, seed=1, device=0):
     arr = None if s_list is None else np.ascontiguousarray(s_list, np.float64)
     _check(lib().clothgpu_selftest_stickmath(device, seed, samples, _p(arr, C.c_double), 0 if arr is None else arr.size,
                                              C.byref(rep)))
+    return rep.as_dict()
+
+
+def selftest_stickmath_f32(device=0):
+    """Exhaustive device self-test of the binary32 stick arithmetic (include/clothgpu.h)."""
+    rep = _abi.StickMathReport()
+    _check(lib().clothgpu_selftest_stickmath_f32(device, C.byref(rep)))
     return rep.as_dict()
 
 

@@ -323,6 +323,9 @@ typedef struct clothgpu_stickmath_report {
 } clothgpu_stickmath_report;
 CLOTHGPU_API int clothgpu_selftest_stickmath(int32_t device, uint64_t seed, uint64_t samples, const double* s_list,
                                 size_t n_list, clothgpu_stickmath_report* report);
+/* The binary32 mode's expansion, EXHAUSTIVELY: every binary32 squared length in [1, 2^63) with every rest length 1..64
+ * that leaves the stick stretched (2.9e10 pairs, about a second) against sqrt.rn.f32 / div.rn.f32. */
+CLOTHGPU_API int clothgpu_selftest_stickmath_f32(int32_t device, clothgpu_stickmath_report* report);
 
 CLOTHGPU_API const char* clothgpu_last_error(void);
 CLOTHGPU_API const char* clothgpu_version(void);

@@ -58,6 +58,14 @@ def test_hard_cases_of_the_reciprocal_step():
     assert rep["mismatches"] == 0, rep
 
 
+def test_binary32_expansion_is_exact_on_every_operand():
+    """The binary32 mode's expansion, exhaustively: every float s in [1, 2^63) with every rest length 1..64 that leaves the
+    stick stretched, against sqrt.rn.f32 / div.rn.f32 — a proof by enumeration, not a sample."""
+    rep = clothgpu.selftest_stickmath_f32()
+    assert rep["tested"] > 2.8e10, rep
+    assert rep["mismatches"] == 0, rep
+
+
 def test_selftest_rejects_operands_outside_its_range():
     with pytest.raises(clothgpu.ClothGpuError):
         clothgpu.selftest_stickmath(s_list=np.array([0.5]))
