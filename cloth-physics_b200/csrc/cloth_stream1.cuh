@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     using L = S1Lane<T>;
     using VL = typename L::vec;                 // 16 bytes of one plane row
     constexpr int NP = L::NP, NC = 2 * NP;      // column pairs / columns per lane
+    // The particle loop as "branch-free common case first, the rule itself only when a lane needs it" (below): +10 % in
+    // binary32, whose launch is bound by issue slots — and -20 % in binary64 (3.88 vs 3.19 ms on 16384^2), whose launch is
+    // paced by the memory system and wants this trip's slots refilled BEFORE the arithmetic.  So: binary32 only.
+    constexpr bool kCommonFirst = sizeof(T) == 4;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     prepare_next_frame_counters(ctr);
@@ -266,48 +270,113 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     int stage = 0;
 #pragma unroll 1
     for (int r = rs; r < re; r += 2) {
-        RowRaw<T> raw0, raw1;
+        RowRaw<T> reg0, reg1;  // RING == 0 only: this trip's rows, in registers
         if (RING == 0) {
             // (a ping-pong of two register sets instead of these copies measured slower: twice the code, worse schedule)
-            raw0 = nxt0, raw1 = nxt1;
-            raw0.fl &= fl_keep, raw1.fl &= fl_keep;
+            reg0 = nxt0, reg1 = nxt1;
+            reg0.fl &= fl_keep, reg1.fl &= fl_keep;
             nxt0 = load_row(r + 2);  // in flight during this trip's arithmetic (rows >= re load nothing)
             nxt1 = load_row(r + 3);
         } else {
             cp_async_wait<RING - 1>();  // the oldest group (this trip) has landed
-            raw0.x = *slot(stage, 0, 0), raw0.y = *slot(stage, 0, 1), raw0.px = *slot(stage, 0, 2), raw0.py = *slot(stage, 0, 3);
-            raw1.x = *slot(stage, 1, 0), raw1.y = *slot(stage, 1, 1), raw1.px = *slot(stage, 1, 2), raw1.py = *slot(stage, 1, 3);
-            raw0.fl = fq[0] & fl_keep, raw1.fl = fq[1] & fl_keep;
+            if (!kCommonFirst) {  // binary64: this trip's rows move to registers and their slots are refilled at once
+                reg0.x = *slot(stage, 0, 0), reg0.y = *slot(stage, 0, 1), reg0.px = *slot(stage, 0, 2), reg0.py = *slot(stage, 0, 3);
+                reg1.x = *slot(stage, 1, 0), reg1.y = *slot(stage, 1, 1), reg1.px = *slot(stage, 1, 2), reg1.py = *slot(stage, 1, 3);
+                reg0.fl = fq[0] & fl_keep, reg1.fl = fq[RING ? 1 : 0] & fl_keep;
+#pragma unroll
+                for (int k = 0; k + 1 < RING; ++k) fq[2 * k] = fq[2 * k + 2], fq[2 * k + 1] = fq[2 * k + 3];
+                issue_trip(r + 2 * RING, stage);  // refill the slots just read (always commits, so group counting stays uniform)
+                fq[RING ? 2 * RING - 2 : 0] = load_flags(r + 2 * RING), fq[RING ? 2 * RING - 1 : 0] = load_flags(r + 2 * RING + 1);
+                stage = stage + 1 == RING ? 0 : stage + 1;
+            }
+        }
+        const uint32_t fl_q[2] = {(RING && kCommonFirst) ? fq[0] & fl_keep : reg0.fl, (RING && kCommonFirst) ? fq[RING ? 1 : 0] & fl_keep : reg1.fl};
+        // row q of the trip as loaded: from the ring slots (they stay valid until the refill below) or from the registers
+        auto fetch_row = [&](int q) -> RowRaw<T> {
+            RowRaw<T> rw;
+            if (RING == 0 || !kCommonFirst) {
+                rw = q ? reg1 : reg0;
+            } else {
+                rw.x = *slot(stage, q, 0), rw.y = *slot(stage, q, 1), rw.px = *slot(stage, q, 2), rw.py = *slot(stage, q, 3);
+                rw.fl = fl_q[q];
+            }
+            return rw;
+        };
+        V2 E[2][NP], O[2][NP];
+        uint32_t fe[2][NP], fo[2][NP];
+        // ---- loop over particles, cloth.go:92-94.  kCommonFirst: first the branch-free common case for all particles of
+        // ---- the trip (particle_update_common); if any lane of the warp has a pinned particle, one within the mouse's reach
+        // ---- or one leaving the window — rare — the rule itself re-runs on the kept inputs.  Otherwise: the rule itself.
+        VL vpx[2], vpy[2];
+        bool rare = !kCommonFirst;
+        if (kCommonFirst) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const RowRaw<T> rw = fetch_row(q);
+            vpx[q] = rw.px, vpy[q] = rw.py;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                E[q][p].x = L::get(rw.x, 2 * p), O[q][p].x = L::get(rw.x, 2 * p + 1);
+                E[q][p].y = L::get(rw.y, 2 * p), O[q][p].y = L::get(rw.y, 2 * p + 1);
+                fe[q][p] = (rw.fl >> (16 * p)) & 0xffu, fo[q][p] = (rw.fl >> (16 * p + 8)) & 0xffu;
+                T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
+                // (rows / columns that do not exist hold zeros and zero flags: whatever the common case computes for them is
+                //  discarded below — they are never stored — but they must not drag the warp into the rare path)
+                const bool r0 = particle_update_common(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u);
+                const bool r1 = particle_update_common(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u);
+                const bool row_ok = r + q < re;
+                rare |= (r0 && row_ok && ce + 2 * p < g.nx) || (r1 && row_ok && ce + 2 * p + 1 < g.nx);
+                L::set(vpx[q], 2 * p, px0), L::set(vpx[q], 2 * p + 1, px1), L::set(vpy[q], 2 * p, py0), L::set(vpy[q], 2 * p + 1, py1);
+            }
+        }
+        }
+        if (!kCommonFirst || __any_sync(FULL, rare)) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const RowRaw<T> rw = fetch_row(q);  // the kept inputs
+                vpx[q] = rw.px, vpy[q] = rw.py;
+                const bool row_ok = r + q < re && ex_e;
+                const bool counted = own_cols && r + q >= ra && r + q < rb;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    E[q][p].x = L::get(rw.x, 2 * p), O[q][p].x = L::get(rw.x, 2 * p + 1);
+                    E[q][p].y = L::get(rw.y, 2 * p), O[q][p].y = L::get(rw.y, 2 * p + 1);
+                    fe[q][p] = (rw.fl >> (16 * p)) & 0xffu, fo[q][p] = (rw.fl >> (16 * p + 8)) & 0xffu;
+                    if (row_ok) {
+                        const uint32_t fe_in = fe[q][p], fo_in = fo[q][p];
+                        T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
+                        if (NP == 1 || ce + 2 * p < g.nx) particle_update(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u);
+                        if (ce + 2 * p + 1 < g.nx) particle_update(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u);
+                        L::set(vpx[q], 2 * p, px0), L::set(vpx[q], 2 * p + 1, px1), L::set(vpy[q], 2 * p, py0), L::set(vpy[q], 2 * p + 1, py1);
+                        if (counted) events.note2(fe_in, fe[q][p], fo_in, fo[q][p]);
+                    }
+                }
+            }
+        } else {
+            // the common case wrote every lane, also the particles that do not exist (zero-filled rows past the chunk, the
+            // row padding): back to the zeros they were loaded as (their flag bytes are zero either way)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const bool row_ok = r + q < re;
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (!(row_ok && ce + c < g.nx)) {
+                        V2& pt = (c & 1) ? O[q][c >> 1] : E[q][c >> 1];
+                        pt.x = pt.y = T(0);
+                        L::set(vpx[q], c, T(0)), L::set(vpy[q], c, T(0));
+                    }
+            }
+        }
+        if (RING != 0 && kCommonFirst) {
 #pragma unroll
             for (int k = 0; k + 1 < RING; ++k) fq[2 * k] = fq[2 * k + 2], fq[2 * k + 1] = fq[2 * k + 3];
             issue_trip(r + 2 * RING, stage);  // refill the slots just read (always commits, so group counting stays uniform)
             fq[2 * RING - 2] = load_flags(r + 2 * RING), fq[2 * RING - 1] = load_flags(r + 2 * RING + 1);
             stage = stage + 1 == RING ? 0 : stage + 1;
         }
-        V2 E[2][NP], O[2][NP];
-        uint32_t fe[2][NP], fo[2][NP];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {  // ---- loop over particles, cloth.go:92-94
-            const RowRaw<T>& rw = q ? raw1 : raw0;
-            VL vpx = rw.px, vpy = rw.py;
-            const bool row_ok = r + q < re && ex_e;
-            const bool counted = own_cols && r + q >= ra && r + q < rb;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                E[q][p].x = L::get(rw.x, 2 * p), O[q][p].x = L::get(rw.x, 2 * p + 1);
-                E[q][p].y = L::get(rw.y, 2 * p), O[q][p].y = L::get(rw.y, 2 * p + 1);
-                fe[q][p] = (rw.fl >> (16 * p)) & 0xffu, fo[q][p] = (rw.fl >> (16 * p + 8)) & 0xffu;
-                if (row_ok) {
-                    const uint32_t fe_in = fe[q][p], fo_in = fo[q][p];
-                    T px0 = L::get(vpx, 2 * p), px1 = L::get(vpx, 2 * p + 1), py0 = L::get(vpy, 2 * p), py1 = L::get(vpy, 2 * p + 1);
-                    if (NP == 1 || ce + 2 * p < g.nx) particle_update(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u);
-                    if (ce + 2 * p + 1 < g.nx) particle_update(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u);
-                    L::set(vpx, 2 * p, px0), L::set(vpx, 2 * p + 1, px1), L::set(vpy, 2 * p, py0), L::set(vpy, 2 * p + 1, py1);
-                    if (counted) events.note2(fe_in, fe[q][p], fo_in, fo[q][p]);
-                }
-            }
-            if (row_ok) store_prev(r + q, vpx, vpy);
-        }
+        for (int q = 0; q < 2; ++q)
+            if (r + q < re && ex_e) store_prev(r + q, vpx[q], vpy[q]);
         const bool own_r[2] = {r >= ra && r < rb, r + 1 >= ra && r + 1 < rb};
         bool touched = false;
 #if defined(S1_NO_MATH)  // timing experiment only: what the memory system gives this access pattern without the sticks

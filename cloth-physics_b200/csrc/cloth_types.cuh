@@ -63,6 +63,7 @@ struct FrameU {
     T s_drag;          // dist < tearDistance  <=>  dist^2 sum < s_drag  (exact, see frame_fold.h)
     T s_pin;           // dist < ClothPinDist(4)
     T s_focus;         // dist < focusArea
+    T s_near;          // max of the three thresholds above: a particle with dist^2 sum >= s_near is out of the mouse's reach
     T fric;            // slider "friction" widened from float32       particle.go:82
     T gx, gy;          // posX, posY = v * (dt*dt)                      particle.go:152-155
     T W, H;            // window size as REAL                           particle.go:164,172
@@ -269,6 +270,23 @@ __device__ __forceinline__ void particle_update(T& x, T& y, T& px, T& py, uint32
         y = T(0);
         py = y;
     }
+}
+
+// The common case of particle_update — not pinned, out of the mouse's reach, still inside the window after the step —
+// without any of the rule's branches: the caller keeps the inputs, calls this, and when ANY lane of the warp reports
+// true re-runs particle_update on the kept inputs of the lanes that do (the mouse touches a handful of particles per
+// frame, pins are the cloth's top row, the window clamp an event).  Where it returns false the values written are
+// exactly particle_update's: same operations in the same order, none of the branches taken.
+template <typename T>
+__device__ __forceinline__ bool particle_update_common(T& x, T& y, T& px, T& py, uint32_t& fl, const FrameU<T>& u) {
+    const T dx = x - u.mx, dy = y - u.my;
+    const T s = dx * dx + dy * dy;
+    const T nx = x + (x - px) * u.fric + u.gx;  // :159
+    const T ny = y + (y - py) * u.fric + u.gy;  // :160
+    const bool rare = (fl & CLOTHGPU_FLAG_PIN) || s < u.s_near || !(nx < u.W) || nx < T(0) || !(ny <= u.H) || ny < T(0);
+    px = x, py = y, x = nx, y = ny;
+    fl &= ~(uint32_t)CLOTHGPU_FLAG_HIGHLIGHT;
+    return rare;
 }
 
 // (*constraint).Update, physics/constraint.go:25-54, on a stick known to be live (still in the

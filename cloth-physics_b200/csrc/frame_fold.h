@@ -5,6 +5,7 @@
 // widened to REAL at the point of use, physics/particle.go:78-83), so the folded values are the ones
 // every particle would have computed for itself.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <limits>
 
@@ -69,6 +70,7 @@ inline FrameU<T> fold_frame(const clothgpu_frame& f, int spacing) {
     u.s_drag = sqrt_lt_threshold<T>(tearDistance);
     u.s_pin = sqrt_lt_threshold<T>((T)4);  // consts.ClothPinDist
     u.s_focus = sqrt_lt_threshold<T>((T)focusArea);
+    u.s_near = std::max(u.s_drag, std::max(u.s_pin, u.s_focus));
     u.fric = friction;
     // :152-155 with vx = vy = 0 at frame start (:180)
     const T dt = (T)f.dt;
