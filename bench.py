@@ -36,7 +36,7 @@ BYTES_PER_PARTICLE_F32 = 33.1
 FP64_INSTR_PER_RELAX = 32.0     # binary64-pipe thread instructions per stretched stick (31 + the rest-length test), DESIGN.md §3.1
 FP64_PIPE_PEAK = 1.8e13         # thread-instructions/s measured by tools/pipe_peaks.cu on B200 (profiles/README.md)
 MIN_TIMED_S = 0.5
-MAX_BLOCKS = 48
+MAX_BLOCKS = 160
 
 WORKLOADS = {
     # name: (nx, ny, sweeps, cloths per GPU [0 = one cloth in row strips over the ranks], pin rule, trace, description)
