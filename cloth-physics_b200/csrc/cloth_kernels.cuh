@@ -292,6 +292,12 @@ __device__ __forceinline__ void segment_quad(const float4 s, float line_width, f
 #ifndef SEG_MIN_BLOCKS
 #define SEG_MIN_BLOCKS 4
 #endif
+#ifndef SEG_PREFETCH2
+#define SEG_PREFETCH2 0
+#endif
+#ifndef SEG_FULL_FAST
+#define SEG_FULL_FAST 1
+#endif
 template <typename T, bool QUADS>
 __global__ void __launch_bounds__(kStreamThreads, SEG_MIN_BLOCKS)
     segment_export_kernel(Planes<T> P, Geom g, int cloth, unsigned long long* __restrict__ status, unsigned long long* ticket,
@@ -390,6 +396,10 @@ __global__ void __launch_bounds__(kStreamThreads, SEG_MIN_BLOCKS)
     };
 
     Trip cur = fetch(0);  // in flight during the look-back below
+#if SEG_PREFETCH2
+    Trip ahead = cur;     // the trip after the next one: two trips of loads in flight
+    if (1 < kTrips) ahead = fetch(1);
+#endif
     if (w == 0) {   // ---- decoupled look-back: where this block's sticks start in the list ------------------------------------
         unsigned long long block_total = 0;
         for (int k = 0; k < kWarps; ++k) block_total += warp_tot[k];
@@ -439,8 +449,13 @@ __global__ void __launch_bounds__(kStreamThreads, SEG_MIN_BLOCKS)
 #pragma unroll 1
     for (int trip = 0; trip < kTrips; ++trip) {
         if (trip * 32 >= n_here) break;  // warp-uniform
+#if SEG_PREFETCH2
+        Trip nxt = ahead;
+        if (trip + 2 < kTrips) ahead = fetch(trip + 2);
+#else
         Trip nxt = cur;
         if (trip + 1 < kTrips) nxt = fetch(trip + 1);  // its loads are in flight while this trip is written out
+#endif
         const bool v = (cur.fl3 & kV) != 0, h = (cur.fl3 & kH) != 0;
         const uint32_t bv = __ballot_sync(0xffffffffu, v), bh = __ballot_sync(0xffffffffu, h);
         const unsigned int total = __popc(bv) + __popc(bh);
@@ -449,8 +464,30 @@ __global__ void __launch_bounds__(kStreamThreads, SEG_MIN_BLOCKS)
             // head of the horizontal stick = the lane to the left (lane 0: loaded separately)
             float xl = __shfl_up_sync(0xffffffffu, x2, 1), yl = __shfl_up_sync(0xffffffffu, y2, 1);
             if (lane == 0) xl = (float)cur.xl0, yl = (float)cur.yl0;
-            unsigned int r = __popc(bv & below) + __popc(bh & below);  // lane l's sticks come after those of lanes < l
             const uint32_t hl_own = cur.fl3 & CLOTHGPU_FLAG_HIGHLIGHT;
+#if SEG_FULL_FAST
+            if ((bv & bh) == 0xffffffffu && run + 64u <= cap32) {
+                // every lane lists both of its sticks (an intact piece of cloth: nearly every trip): lane l's pair goes to
+                // run + 2l, run + 2l + 1 — no ranking, no staging, each lane stores 32 (64) contiguous bytes
+                const unsigned int o = run + 2u * lane;
+                const float4 sv = make_float4((float)cur.xu, (float)cur.yu, x2, y2), sh = make_float4(xl, yl, x2, y2);
+                s_hl[w][hl_at + 2u * lane] = (hl_own & (cur.fl3 >> 8)) != 0;
+                s_hl[w][hl_at + 2u * lane + 1u] = (hl_own & (cur.fl3 >> 16)) != 0;
+                if (QUADS) {
+                    float4 q0, q1, q2, q3;
+                    segment_quad(sv, line_width, q0, q1);
+                    segment_quad(sh, line_width, q2, q3);
+                    out[2ull * o] = q0, out[2ull * o + 1] = q1, out[2ull * o + 2] = q2, out[2ull * o + 3] = q3;
+                } else {
+                    out[o] = sv, out[o + 1] = sh;
+                    if (idx) idx[o] = make_uint2(cur.tail - g.nx, cur.tail), idx[o + 1] = make_uint2(cur.tail - 1, cur.tail);
+                }
+                run += 64u, hl_at += 64u;
+                cur = nxt;
+                continue;
+            }
+#endif
+            unsigned int r = __popc(bv & below) + __popc(bh & below);  // lane l's sticks come after those of lanes < l
             if (v) {
                 s_xy[w][r] = make_float4((float)cur.xu, (float)cur.yu, x2, y2);
                 s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 8)) != 0;  // cloth.go:127-128: both ends highlighted
