@@ -103,9 +103,11 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     using VL = typename L::vec;                 // 16 bytes of one plane row
     constexpr int NP = L::NP, NC = 2 * NP;      // column pairs / columns per lane
     // The particle loop as "branch-free common case first, the rule itself only when a lane needs it" (below): +10 % in
-    // binary32, whose launch is bound by issue slots — and -20 % in binary64 (3.88 vs 3.19 ms on 16384^2), whose launch is
-    // paced by the memory system and wants this trip's slots refilled BEFORE the arithmetic.  So: binary32 only.
+    // binary32, whose launch is bound by issue slots — and -20 % to -32 % in binary64 (3.88 / 4.17 vs 3.15-3.19 ms on
+    // 16384^2 with the slots refilled after / before the arithmetic): keeping the inputs for the rare path costs 16
+    // registers the binary64 kernel does not have (88 bytes of spills in the loop).  So: binary32 only.
     constexpr bool kCommonFirst = sizeof(T) == 4;
+    constexpr bool kEarlyRefill = sizeof(T) == 8;  // binary64: a trip's slots are refilled before its arithmetic
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     prepare_next_frame_counters(ctr);
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
             nxt1 = load_row(r + 3);
         } else {
             cp_async_wait<RING - 1>();  // the oldest group (this trip) has landed
-            if (!kCommonFirst) {  // binary64: this trip's rows move to registers and their slots are refilled at once
+            if (kEarlyRefill) {  // binary64: this trip's rows move to registers and their slots are refilled at once
                 reg0.x = *slot(stage, 0, 0), reg0.y = *slot(stage, 0, 1), reg0.px = *slot(stage, 0, 2), reg0.py = *slot(stage, 0, 3);
                 reg1.x = *slot(stage, 1, 0), reg1.y = *slot(stage, 1, 1), reg1.px = *slot(stage, 1, 2), reg1.py = *slot(stage, 1, 3);
                 reg0.fl = fq[0] & fl_keep, reg1.fl = fq[RING ? 1 : 0] & fl_keep;
@@ -290,11 +292,11 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                 stage = stage + 1 == RING ? 0 : stage + 1;
             }
         }
-        const uint32_t fl_q[2] = {(RING && kCommonFirst) ? fq[0] & fl_keep : reg0.fl, (RING && kCommonFirst) ? fq[RING ? 1 : 0] & fl_keep : reg1.fl};
+        const uint32_t fl_q[2] = {(RING && !kEarlyRefill) ? fq[0] & fl_keep : reg0.fl, (RING && !kEarlyRefill) ? fq[RING ? 1 : 0] & fl_keep : reg1.fl};
         // row q of the trip as loaded: from the ring slots (they stay valid until the refill below) or from the registers
         auto fetch_row = [&](int q) -> RowRaw<T> {
             RowRaw<T> rw;
-            if (RING == 0 || !kCommonFirst) {
+            if (RING == 0 || kEarlyRefill) {
                 rw = q ? reg1 : reg0;
             } else {
                 rw.x = *slot(stage, q, 0), rw.y = *slot(stage, q, 1), rw.px = *slot(stage, q, 2), rw.py = *slot(stage, q, 3);
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                     }
             }
         }
-        if (RING != 0 && kCommonFirst) {
+        if (RING != 0 && !kEarlyRefill) {
 #pragma unroll
             for (int k = 0; k + 1 < RING; ++k) fq[2 * k] = fq[2 * k + 2], fq[2 * k + 1] = fq[2 * k + 3];
             issue_trip(r + 2 * RING, stage);  // refill the slots just read (always commits, so group counting stays uniform)
