@@ -110,3 +110,34 @@ def test_packed_ensemble_of_640_cloths(oracle):
     assert g.last_schedule()[1] == "wave_frame_kernel<double,DRAG,PACK>"
     for e, o in oracles.items():
         assert_same_state(g.read_state(cloth=e), o.read_state(), f"packed ensemble, cloth {e} of {E}")
+
+
+def test_packed_ensemble_of_640_cloths_with_a_mouse_per_cloth(oracle):
+    """BASELINE configs[3] as bench.py runs it (`c3`): clothgpu_step_each on the packed wavefront kernel, AUTO schedule,
+    enough cloths for several CTA spans (a span starts in the middle of a cloth, so the entry warps pick up the frame of
+    the cloth they land in).  The frames are bench.py's own per-cloth frames (phase = cloth id)."""
+    import bench
+    nx = ny = 128
+    E, K = 640, 8
+    g = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, ensemble=E, max_iterations=K))
+    one = _abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K)
+    checked = sorted({0, 1, 2, 3, 147, 148, 149, 295, 296, 297, 444, 445, 591, 592, 636, 637, 638, 639} | set(range(16, E, 44)))
+    oracles = {e: oracle.OracleCloth(one, oracle.COLOUR) for e in checked}
+    for e in range(E):
+        st = random_state(nx, ny, seed=9000 + e)
+        g.write_state(*st, cloth=e)
+        if e in oracles:
+            oracles[e].write_state(*st)
+    torn = 0
+    for t in range(3):
+        frames = bench.per_cloth_frames(t, E, nx, ny, K)
+        for f in frames:
+            f.tear_length = 9.5          # the jittered start state tears under the dragged cloths' mice
+        g.step_each(frames)
+        for e, o in oracles.items():
+            o.step(frames[e])
+            torn += o.torn_last
+    assert g.last_schedule()[1] == "wave_frame_kernel<double,PER_CLOTH,PACK>"
+    for e, o in oracles.items():
+        assert_same_state(g.read_state(cloth=e), o.read_state(), f"packed ensemble with per-cloth frames, cloth {e} of {E}")
+    assert torn > 0
