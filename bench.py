@@ -238,6 +238,16 @@ def cpu_run(wl, seconds_target=None, steps=None, warmup=1):
             "frames_per_s": n / dt, "ms_per_frame": 1e3 * dt / n, "seconds": dt, "frames": n}
 
 
+def config_for(wl):
+    """`config` of the JSON line: the workload and nothing else, so that both arms (--impl clothgpu / reference) print the
+    SAME object for the same workload; how an arm ran it (schedule, sharding, the CPU arm's sample) goes into `run`."""
+    nx, ny, K, cloths, pin, trace, desc_txt = WORKLOADS[wl]
+    return {"workload": desc_txt, "name": wl, "nx": nx, "ny": ny, "iterations": K, "pin": pin, "trace": trace,
+            "cloths": "one cloth (row strips over the GPUs when N > 1)" if cloths == 0 else f"{cloths} independent cloths per GPU",
+            "l2": "inputs larger than L2: every frame re-streams the cloth's state from HBM" if nx * ny * max(1, cloths) * 33 > 126e6
+                  else "state fits L2"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (its C restatement, oracle/cloth_oracle.h) on the
     host cores, same metric and config; each step = one frame of a bounded sample of the workload."""
@@ -251,9 +261,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "stick_relaxations_per_sec", "value": r["value"], "unit": "stick relaxations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"],
         "higher_is_better": True, "scaling": "strong" if cloths == 0 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc_txt, "nx": nx0, "ny": ny0, "iterations": K, "pin": pin, "trace": trace,
-                   "sample": f"each step = one frame of ONE {nx}x{ny} cloth on one host core (the reference's physics is one goroutine, "
-                             f"main.go:87-100, and a sequential Gauss-Seidel sweep does not thread)"},
+        "config": config_for(wl),
+        "run": {"sample": f"each step = one frame of ONE {nx}x{ny} cloth on one host core (the reference's physics is one goroutine, "
+                          f"main.go:87-100, and a sequential Gauss-Seidel sweep does not thread)"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "stick relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_sec": r["frames_per_s"],
@@ -691,9 +701,9 @@ def main():
         "metric": "stick_relaxations_per_sec", "value": m["value"], "unit": "stick relaxations/s", "n_gpus": ctx.world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if arm.strips else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": desc_txt, "nx": nx, "ny": ny, "iterations": K, "pin": pin, "trace": trace,
-                   "cloths_per_gpu": (1.0 / ctx.world) if arm.strips else arm.cloths, "schedule": args.schedule,
-                   "l2": f"inputs larger than L2: {arm.particles * arm.bpp / 2 / 1e6:.0f} MB of state per GPU, every frame re-streams it",
+        "config": config_for(wl),
+        "run": {"cloths_per_gpu": (1.0 / ctx.world) if arm.strips else arm.cloths, "schedule": args.schedule,
+                   "l2": f"{arm.particles * arm.bpp / 2 / 1e6:.0f} MB of state per GPU, re-streamed every frame",
                    "sharding": ("row strips, ghost rows 2 x sweeps deep; the frame kernel stores its edge rows into the neighbours' memory (NVLink peer "
                                 "stores) and hand-shakes per edge chunk (ld.acquire.sys / st.release.sys epoch flags): 1 launch per frame, no NCCL on the data path")
                                if arm.strips else "independent cloths per GPU, no data-path collective"},
