@@ -239,16 +239,160 @@ __global__ void __launch_bounds__(kStreamThreads)
 // Sticks are listed in the order Cloth.Init created them (physics/cloth.go:61-70): by TAIL particle in
 // row-major order, the vertical stick (from the particle above) before the horizontal one (from the
 // particle to the left).  A stick is listed when it is still in the slice and both endpoints are
-// active.  ONE launch: every block of kSegBlock consecutive particles counts its sticks from the flag bytes, obtains
-// its place in the list by a decoupled look-back over the blocks before it, and scatters.
-constexpr int kSegPerThread = 16;
-constexpr int kSegBlock = kStreamThreads * kSegPerThread;
+// active.  TWO launches over TILES of kSegBlock consecutive particles of the owned rows in PADDED row-major order
+// (padding columns hold zero flags and add nothing, so the order of the listed sticks is the unpadded one):
+//   segment_plan_kernel    reads the flag bytes only (2 of the 66 bytes per particle the export moves): which sticks every
+//                          tile lists, where they go inside the tile's part of the list, and — by the last block to
+//                          finish — where every tile's part starts;
+//   segment_export_kernel  streams the coordinates and writes the list: with the plan in hand no block waits for another.
+// A cloth of at most kSegSelfPlanTiles tiles (the GUI's) takes ONE launch: every export block plans its own tile and counts the
+// tiles before it.
+constexpr unsigned int kSegSelfPlanTiles = 4;
+#ifndef SEG_PLAN_BLOCKS_PER_SM
+#define SEG_PLAN_BLOCKS_PER_SM 6  // (all blocks of the plan kernel resident at once: 40 registers x 256 threads)
+#endif
+constexpr int kSegThreads = 256, kSegPerThread = 16;
+constexpr int kSegBlock = kSegThreads * kSegPerThread;
 
-// Decoupled look-back status of one block: epoch (29 bits) | flag (2 bits) | value (33 bits).  The epoch is the launch
-// number, so the array is never cleared: a word of an earlier launch simply reads as "nothing yet".
-constexpr unsigned long long kSegFlagAggregate = 1ull, kSegFlagPrefix = 2ull;
-__device__ __forceinline__ unsigned long long seg_status(unsigned int epoch, unsigned long long flag, unsigned long long value) {
-    return ((unsigned long long)(epoch & 0x1fffffffu) << 35) | (flag << 33) | (value & 0x1ffffffffull);
+// The plan of one tile.  Thread t of the planning block owns particles [16 t, 16 t + 16) of the tile; bit i of its masks is
+// particle 16 t + i.  Read back as 32-bit words, word k holds the 32 particles of CHUNK k — the ballots of the export's trips.
+struct __align__(16) SegPlan {
+    uint16_t mv[kSegThreads], mh[kSegThreads];  // the particle lists its vertical / horizontal stick
+    uint16_t hv[kSegThreads], hh[kSegThreads];  // ... and that stick is highlighted (both ends are, cloth.go:127-128)
+    uint16_t pre[kSegThreads];                  // sticks of the tile before particle 16 t
+    uint32_t total, any_hl, pad[2];             // sticks of the tile; whether any of them is highlighted
+};
+static_assert(sizeof(SegPlan) % 16 == 0, "moved by bulk copies");
+
+template <int kThreads>
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* warp_sums, unsigned int& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int up_v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up_v;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    unsigned int before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        const unsigned int t = warp_sums[k];
+        if (k < w) before += t;
+        all += t;
+    }
+    total = all;
+    return before + incl - v;
+}
+
+// The flag bytes of 16 consecutive particles and of the 16 above them (one uint4 each) decide byte-parallel which sticks
+// are listed: tail t lists its vertical stick when t and the particle above are active and that particle's ALIVE_V bit is
+// set, its horizontal stick likewise with the particle to the left.  The four answers per particle are gathered into
+// 16-bit masks.  `fl` = the flag bytes of the owned rows, `off` = the first particle (padded row-major, a multiple of 16),
+// `n` = owned rows * pitch.  Returns the sticks listed, bit 20 set when one of them is highlighted (sums of 256 of these
+// keep both apart: a tile lists at most 8192 sticks).
+constexpr unsigned int kSegCountMask = 0xfffffu;
+struct SegFlags16 {
+    uint4 own, up;
+    uint32_t left;  // flag byte of the particle left of the first one (0 at the start of a row)
+};
+__device__ __forceinline__ SegFlags16 seg_load16(const uint8_t* __restrict__ fl, const Geom& g, unsigned int n, unsigned int off) {
+    SegFlags16 f;
+    f.own = f.up = make_uint4(0, 0, 0, 0), f.left = 0;
+    if (off < n) {
+        const unsigned int pitch = (unsigned int)g.pitch, ly = off / pitch, cx = off - ly * pitch;
+        f.own = *reinterpret_cast<const uint4*>(fl + off);
+        if (g.own_row0 + (int)ly > g.held_row0) f.up = *reinterpret_cast<const uint4*>(fl + off - pitch);  // a ghost row of a strip, or absent at the cloth's top
+        if (cx > 0) f.left = fl[off - 1];
+    }
+    return f;
+}
+__device__ __forceinline__ unsigned int seg_masks16(const SegFlags16& fl16, uint32_t& mv, uint32_t& mh, uint32_t& hv, uint32_t& hh) {
+    constexpr uint32_t k1 = 0x01010101u, kGather = 0x01020408u;  // (m & k1) * kGather >> 24: bit 0 of bytes 0..3 -> bits 0..3
+    mv = mh = hv = hh = 0;
+    uint32_t carry = fl16.left;  // flag byte of the particle left of word q
+    const uint32_t wq[4] = {fl16.own.x, fl16.own.y, fl16.own.z, fl16.own.w}, up[4] = {fl16.up.x, fl16.up.y, fl16.up.z, fl16.up.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t f = wq[q], act = (f >> 1) & k1;
+        const uint32_t lf = (f << 8) | (carry & 0xffu);  // each byte: the flags of its left neighbour
+        const uint32_t v = act & (up[q] >> 4) & (up[q] >> 1) & k1, h = act & (lf >> 3) & (lf >> 1) & k1;
+        mv |= ((v * kGather) >> 24) << (4 * q);
+        mh |= ((h * kGather) >> 24) << (4 * q);
+        hv |= (((v & (f >> 2) & (up[q] >> 2)) * kGather) >> 24) << (4 * q);
+        hh |= (((h & (f >> 2) & (lf >> 2)) * kGather) >> 24) << (4 * q);
+        carry = f >> 24;
+    }
+    return (unsigned int)(__popc(mv) + __popc(mh)) | ((hv | hh) ? (kSegCountMask + 1u) : 0u);
+}
+
+// The plans of the tiles, a few tiles per block (the next tile's flag bytes are in flight while this one's are counted).
+// The last block to finish turns the tiles' totals (left in `starts`, which holds a multiple of 16 entries) into their
+// starts: 4096 tiles per step, every thread 16 consecutive ones.
+__global__ void __launch_bounds__(kSegThreads)
+    segment_plan_kernel(const uint8_t* __restrict__ flags, Geom g, int cloth, SegPlan* __restrict__ plan, unsigned int* __restrict__ starts,
+                        unsigned int n_tiles, unsigned int* done, unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned int warp_sums[kSegThreads / 32];
+    __shared__ bool s_last;
+    const unsigned int n = (unsigned int)g.own_rows * (unsigned int)g.pitch;
+    const uint8_t* fl = flags + (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
+    SegFlags16 next = seg_load16(fl, g, n, blockIdx.x * (unsigned int)kSegBlock + threadIdx.x * 16u);
+    for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const SegFlags16 cur = next;
+        if (tile + gridDim.x < n_tiles) next = seg_load16(fl, g, n, (tile + gridDim.x) * (unsigned int)kSegBlock + threadIdx.x * 16u);
+        uint32_t mv, mh, hv, hh;
+        const unsigned int v = seg_masks16(cur, mv, mh, hv, hh);
+        unsigned int all;
+        const unsigned int before = block_exclusive_scan<kSegThreads>(v, warp_sums, all);
+        SegPlan& mine = plan[tile];
+        mine.mv[threadIdx.x] = (uint16_t)mv, mine.mh[threadIdx.x] = (uint16_t)mh;
+        mine.hv[threadIdx.x] = (uint16_t)hv, mine.hh[threadIdx.x] = (uint16_t)hh;
+        mine.pre[threadIdx.x] = (uint16_t)(before & kSegCountMask);
+        if (threadIdx.x == 0) {
+            mine.total = all & kSegCountMask, mine.any_hl = all >> 20;
+            starts[tile] = all & kSegCountMask;  // (turned into the tile's start below)
+        }
+        __syncthreads();  // warp_sums is reused by the next tile
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- the last block: exclusive prefix over the tiles' totals ---------------------------------------------------------------
+    __threadfence();
+    unsigned int carried = 0;
+    for (unsigned int lo = 0; lo < n_tiles; lo += kSegThreads * 16u) {
+        const unsigned int at = lo + threadIdx.x * 16u;
+        uint4 t4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            t4[j] = make_uint4(0, 0, 0, 0);
+            if (at + 4u * j < n_tiles) t4[j] = __ldcg(reinterpret_cast<const uint4*>(starts + at) + j);
+        }
+        unsigned int t[16], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[4 * j] = t4[j].x, t[4 * j + 1] = t4[j].y, t[4 * j + 2] = t4[j].z, t[4 * j + 3] = t4[j].w;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (at + i >= n_tiles) t[i] = 0;  // (entries behind the last tile are not initialised)
+            sum += t[i];
+        }
+        unsigned int chunk_total;
+        unsigned int run = carried + block_exclusive_scan<kSegThreads>(sum, warp_sums, chunk_total);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const unsigned int mine_i = t[i];
+            t[i] = run, run += mine_i;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (at + 4u * j < n_tiles) reinterpret_cast<uint4*>(starts + at)[j] = make_uint4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+        carried += chunk_total;
+        __syncthreads();  // warp_sums is reused by the next step
+    }
+    if (threadIdx.x == 0) *total_out = carried, *done = 0u;  // (the counter is ready for the next export)
 }
 
 // addSegment / normal of the reference's render loops (physics/cloth.go:150-168) for one stick a -> b: the four float32
@@ -277,259 +421,244 @@ __device__ __forceinline__ void segment_quad(const float4 s, float line_width, f
     q1 = make_float4(s.z - nx, s.w - ny, s.x - nx, s.y - ny);
 }
 
-// One block per kSegBlock particles of the owned rows in PADDED row-major order (padding columns hold zero flags and add
-// nothing, so the order of the listed sticks is the unpadded one); blocks take their index from a ticket counter, so a
-// block's predecessors are always running or done.  Every warp owns 512 consecutive particles.  It loads their flag
-// bytes and those of the row above once (16 bytes per lane), keeps them in shared memory and counts the sticks with
-// byte-parallel tests: tail t lists its vertical stick when t and the particle above are active and that particle's
-// ALIVE_V bit is set, its horizontal stick likewise with the particle to the left.  Warp 0 publishes the block's count,
-// sums the counts of the blocks before it (decoupled look-back, 32 blocks per step) and publishes the inclusive prefix;
-// from there on the warps run independently: 32 particles per trip, flags from shared memory, the coordinate loads of
-// the next trip in flight while this trip's sticks are ranked with two ballots, converted and staged in a warp-private
-// buffer at their rank, then copied out as ONE contiguous, fully coalesced run (before ranking the sticks of consecutive
-// lanes are not adjacent in the output: a lane has 0, 1 or 2 of them).  QUADS: the run is written as outline quads
-// (2 float4 per stick, addSegment) instead of endpoint pairs.
+// One block per tile.  The plan arrives by one bulk copy; every warp owns 512 consecutive particles (16 chunks) and a
+// private ring of kSegStages buffers in shared memory, each holding x, y of kSegStageN consecutive particles and of the
+// kSegStageN above them, which one lane hands to the TMA engine — four bulk copies per buffer, completing on the buffer's
+// mbarrier — the moment the block starts: kSegStages * kSegStageN * 32 bytes in flight per warp at no register cost,
+// refilled as soon as a buffer has been consumed.  Per chunk: its two masks and its coordinates from shared memory, the
+// particle to the left by shuffle.  An intact piece of cloth — nearly every chunk — stores lane l's two sticks straight to
+// run + 2l, run + 2l + 1; otherwise the sticks are ranked with the masks, staged in a warp-private buffer at their rank
+// and copied out as ONE contiguous, coalesced run.  QUADS: outline quads (2 float4 per stick, addSegment) instead of
+// endpoint pairs; IDX: the particle indices of every stick's ends as well.  Highlight bytes: all zero for nearly every
+// tile and then written as such; otherwise assembled in shared memory and written as 128-bit stores shifted so that shared
+// and global addresses agree mod 16.
 #ifndef SEG_MIN_BLOCKS
-#define SEG_MIN_BLOCKS 4
+#define SEG_MIN_BLOCKS 3
 #endif
-#ifndef SEG_PREFETCH2
-#define SEG_PREFETCH2 0
+#ifndef SEG_STAGE_N
+#define SEG_STAGE_N 64
+#endif
+#ifndef SEG_STAGES
+#define SEG_STAGES 3  // (measured on 4096^2: 3 buffers x 3 blocks per SM 152 us, 2 x 4 156 us, 4 x 32 particles 160 us)
 #endif
 #ifndef SEG_FULL_FAST
 #define SEG_FULL_FAST 1
 #endif
-template <typename T, bool QUADS>
-__global__ void __launch_bounds__(kStreamThreads, SEG_MIN_BLOCKS)
-    segment_export_kernel(Planes<T> P, Geom g, int cloth, unsigned long long* __restrict__ status, unsigned long long* ticket,
-                          unsigned long long ticket_base, unsigned int epoch, unsigned int n_blocks, float line_width,
-                          float4* __restrict__ out, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
-                          unsigned long long cap, unsigned long long* __restrict__ total_out) {
-    constexpr int kWarps = kStreamThreads / 32, kPerWarp = kSegBlock / kWarps, kTrips = kPerWarp / 32;
-    static_assert(kPerWarp == 32 * 16, "one uint4 of flag bytes per lane");
-    __shared__ unsigned int warp_tot[kWarps];
-    __shared__ unsigned int s_bid;
-    __shared__ unsigned long long s_excl;
-    __shared__ __align__(16) uint8_t s_f[kWarps][kPerWarp + 16];   // [15] = the particle left of the warp's first one
-    __shared__ __align__(16) uint8_t s_fu[kWarps][kPerWarp];
+constexpr int kSegStageN = SEG_STAGE_N, kSegStages = SEG_STAGES;
+// dynamic shared memory of the export kernel: the warps' coordinate rings
+template <typename T>
+constexpr size_t seg_smem_bytes() {
+    return (size_t)(kSegThreads / 32) * kSegStages * 4 * kSegStageN * sizeof(T);
+}
+template <typename T, bool QUADS, bool IDX>
+__global__ void __launch_bounds__(kSegThreads, SEG_MIN_BLOCKS)
+    segment_export_kernel(Planes<T> P, Geom g, int cloth, const SegPlan* __restrict__ plan, const unsigned int* __restrict__ starts,
+                          float line_width, float4* __restrict__ out, uint8_t* __restrict__ hl, uint2* __restrict__ idx,
+                          unsigned long long cap, unsigned int n_tiles, unsigned long long* __restrict__ total_out) {
+    constexpr int kWarps = kSegThreads / 32;
+    constexpr int kPerWarp = kSegBlock / kWarps, kFills = kPerWarp / kSegStageN, kTripsPerFill = kSegStageN / 32;
+    static_assert(kPerWarp % kSegStageN == 0 && kSegStageN % 32 == 0, "whole chunks per buffer, 16-byte copies");
+    __shared__ SegPlan s_plan;
+    __shared__ __align__(8) unsigned long long s_bar_plan, s_bar[kWarps][kSegStages];  // one mbarrier per warp and ring buffer
     __shared__ float4 s_xy[kWarps][64];
-    __shared__ uint2 s_idx[kWarps][64];
-    // the highlight bytes of all sticks of the warp (at most 1024), shifted so that shared and global addresses agree
-    // mod 16: they leave as 128-bit stores at the end instead of two one-byte stores per lane and trip
-    __shared__ __align__(16) uint8_t s_hl[kWarps][2 * kPerWarp + 16];
+    __shared__ uint2 s_idx[IDX ? kWarps : 1][64];
+    __shared__ __align__(16) uint8_t s_hl[2 * kSegBlock + 16];
+    extern __shared__ __align__(16) unsigned char seg_dyn[];
     const long long n = (long long)g.own_rows * g.pitch;
     const long long base = (long long)cloth * g.cloth_stride + (long long)(g.own_row0 - g.held_row0) * g.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t below = (1u << lane) - 1u;
-    if (threadIdx.x == 0) s_bid = (unsigned int)(atomicAdd(ticket, 1ull) - ticket_base);
+    const unsigned int bid = blockIdx.x;
+    const long long tile_first = (long long)bid * kSegBlock;
+    const int n_tile = (int)min((long long)kSegBlock, n - tile_first);  // particles of this tile
+    const T* X = P.x + base + tile_first;
+    const T* Y = P.y + base + tile_first;
+    const int pitch = g.pitch;
+    if (lane == 0) {
+        if (w == 0) mbar_init(&s_bar_plan, 1);
+        for (int d = 0; d < kSegStages; ++d) mbar_init(&s_bar[w][d], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const unsigned int bid = s_bid;
-    const long long warp_first = (long long)bid * kSegBlock + (long long)w * kPerWarp;
-    const uint8_t* fl = P.fl + base;
-    const T* X = P.x + base;
-    const T* Y = P.y + base;
 
-    {   // ---- flags of this warp's 512 particles -> shared memory; their sticks ---------------------------------------------
-        constexpr uint32_t k1 = 0x01010101u;
-        const long long off = warp_first + lane * 16;
-        unsigned int cnt = 0;
-        uint4 w4 = make_uint4(0, 0, 0, 0), u4 = make_uint4(0, 0, 0, 0);
-        uint32_t left = 0;
-        if (off < n) {
-            const int ly = (int)(off / g.pitch), cx = (int)(off - (long long)ly * g.pitch);
-            w4 = *reinterpret_cast<const uint4*>(fl + off);
-            if (g.own_row0 + ly > g.held_row0) u4 = *reinterpret_cast<const uint4*>(fl + off - g.pitch);  // a ghost row of a strip, or absent at the cloth's top
-            if (cx > 0) left = fl[off - 1];
-            const uint32_t wq[4] = {w4.x, w4.y, w4.z, w4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
-            uint32_t carry = left;  // flag byte of the particle left of word q
+    // ---- the warp's coordinate ring ------------------------------------------------------------------------------------------
+    T* const ring = reinterpret_cast<T*>(seg_dyn) + (size_t)w * kSegStages * 4 * kSegStageN;  // [stage][x | y | xu | yu][kSegStageN]
+    const int warp_lo = w * kPerWarp;        // first particle of the warp in the tile
+    const int warp_n = n_tile - warp_lo;     // particles of the tile from there on (<= 0: none for this warp)
+    // the row above the first held row does not exist (no stick hangs from it either: those shared bytes stay unread)
+    const int warp_no_up = g.own_row0 > g.held_row0 ? 0 : (int)max(0ll, min((long long)kPerWarp, (long long)pitch - (tile_first + warp_lo)));
+    // fill number f of the warp = particles [warp_lo + f * kSegStageN, + kSegStageN) of the tile -> buffer f % kSegStages
+    auto fill_count = [&](int f) { return max(0, min(kSegStageN, warp_n - f * kSegStageN)); };  // (a multiple of 16)
+    auto issue_fill = [&](int f) {  // one lane
+        const int cnt = fill_count(f);
+        if (cnt <= 0) return;
+        const int at = warp_lo + f * kSegStageN;
+        const int no_up = max(0, min(cnt, warp_no_up - f * kSegStageN));
+        T* const buf = ring + (size_t)(f % kSegStages) * 4 * kSegStageN;
+        unsigned long long* const bar = &s_bar[w][f % kSegStages];
+        mbar_arrive_expect_tx(bar, (unsigned)((2 * cnt + 2 * (cnt - no_up)) * (int)sizeof(T)));
+        bulk_g2s(buf, X + at, (unsigned)(cnt * (int)sizeof(T)), bar);
+        bulk_g2s(buf + kSegStageN, Y + at, (unsigned)(cnt * (int)sizeof(T)), bar);
+        if (cnt > no_up) {
+            bulk_g2s(buf + 2 * kSegStageN + no_up, X + at + no_up - pitch, (unsigned)((cnt - no_up) * (int)sizeof(T)), bar);
+            bulk_g2s(buf + 3 * kSegStageN + no_up, Y + at + no_up - pitch, (unsigned)((cnt - no_up) * (int)sizeof(T)), bar);
+        }
+    };
+    // the particle left of the warp's first one (head of lane 0's horizontal stick in its first chunk)
+    float carry_x = 0.f, carry_y = 0.f;
+    T carry_tx = T(0), carry_ty = T(0);  // (converted when first used: the load stays off the warp's critical path)
+    if (lane == 0) {
+        if (w == 0 && plan) {
+            mbar_arrive_expect_tx(&s_bar_plan, (unsigned)sizeof(SegPlan));
+            bulk_g2s(&s_plan, plan + bid, (unsigned)sizeof(SegPlan), &s_bar_plan);
+        }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t f = wq[q], act = (f >> 1) & k1;
-                const uint32_t fl_left = (f << 8) | (carry & 0xffu);  // each byte: the flags of its left neighbour
-                cnt += __popc(act & (up[q] >> 4) & (up[q] >> 1) & k1) + __popc(act & (fl_left >> 3) & (fl_left >> 1) & k1);
-                carry = f >> 24;
-            }
-        }
-        *reinterpret_cast<uint4*>(&s_f[w][16 + lane * 16]) = w4;
-        *reinterpret_cast<uint4*>(&s_fu[w][lane * 16]) = u4;
-        if (lane == 0) s_f[w][15] = (uint8_t)left;  // (0 when the first particle starts a row: no stick to its left)
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-        if (lane == 0) warp_tot[w] = cnt;
+        for (int f = 0; f < kSegStages && f < kFills; ++f) issue_fill(f);
+        if (warp_n > 0 && tile_first + warp_lo > 0) carry_tx = X[warp_lo - 1], carry_ty = Y[warp_lo - 1];
     }
-    __syncthreads();
-    // rows and columns in 32-bit arithmetic: one division per lane, then every trip advances the lane by 32 particles
-    const int row0 = (int)(warp_first / g.pitch), cx0 = (int)(warp_first - (long long)row0 * g.pitch);
-    const int n_here = (int)min((long long)kPerWarp, n - warp_first);  // particles of this warp (<= 0: none)
-    X += warp_first, Y += warp_first;
-    const unsigned int pitch = (unsigned int)g.pitch;
-    unsigned int f_cx = (unsigned int)(cx0 + lane) % pitch;                     // column / tail index of the lane's particle
-    unsigned int f_tail = (unsigned int)(row0 + (cx0 + lane) / (int)pitch) * (unsigned int)g.nx + f_cx;  // in the NEXT fetch
-
-    constexpr uint32_t kV = 1u << 24, kH = 1u << 25;
-    struct Trip {
-        T x, y, xu, yu, xl0, yl0;  // own position, the particle above, the particle left of lane 0's
-        uint32_t fl3;              // flag bytes: own | above << 8 | left << 16; kV / kH = the lane lists that stick
-        unsigned int tail;         // index of the particle in the (unpadded) cloth
-    };
-    auto fetch = [&](int trip) -> Trip {
-        Trip t;
-        t.x = t.y = t.xu = t.yu = t.xl0 = t.yl0 = T(0);
-        t.fl3 = 0u, t.tail = f_tail;
-        const int li = trip * 32 + lane;
-        if (li < n_here) {
-            const uint32_t f = s_f[w][16 + li];
-            t.fl3 = f;
-            if (f & CLOTHGPU_FLAG_ACTIVE) {
-                const uint32_t fu = s_fu[w][li], fw = f_cx > 0 ? s_f[w][15 + li] : 0u;
-                t.fl3 |= (fu << 8) | (fw << 16);
-                if ((fu & (CLOTHGPU_FLAG_ALIVE_V | CLOTHGPU_FLAG_ACTIVE)) == (CLOTHGPU_FLAG_ALIVE_V | CLOTHGPU_FLAG_ACTIVE)) t.fl3 |= kV;
-                if ((fw & (CLOTHGPU_FLAG_ALIVE_H | CLOTHGPU_FLAG_ACTIVE)) == (CLOTHGPU_FLAG_ALIVE_H | CLOTHGPU_FLAG_ACTIVE)) t.fl3 |= kH;
-            }
-            // every lane loads its own position (its right neighbour may need it as the head of a horizontal stick)
-            t.x = X[li], t.y = Y[li];
-            if (t.fl3 & kV) t.xu = X[li - (int)pitch], t.yu = Y[li - (int)pitch];
-            if (lane == 0 && (t.fl3 & kH)) t.xl0 = X[li - 1], t.yl0 = Y[li - 1];
-        }
-        // the lane's particle of the next trip: 32 further on, rows are `pitch` apart and hold nx particles
-        f_cx += 32, f_tail += 32;
-        while (f_cx >= pitch) f_cx -= pitch, f_tail += (unsigned int)g.nx - pitch;
-        return t;
-    };
-
-    Trip cur = fetch(0);  // in flight during the look-back below
-#if SEG_PREFETCH2
-    Trip ahead = cur;     // the trip after the next one: two trips of loads in flight
-    if (1 < kTrips) ahead = fetch(1);
-#endif
-    if (w == 0) {   // ---- decoupled look-back: where this block's sticks start in the list ------------------------------------
-        unsigned long long block_total = 0;
-        for (int k = 0; k < kWarps; ++k) block_total += warp_tot[k];
-        volatile unsigned long long* st = status;
-        if (lane == 0) {
-            st[bid] = seg_status(epoch, bid == 0 ? kSegFlagPrefix : kSegFlagAggregate, block_total);
-            __threadfence();
-        }
-        unsigned long long excl = 0;
-        long long look = (long long)bid - 1;  // nearest predecessor this step looks at (lane 0)
-        while (look >= 0) {
-            const long long at = look - lane;
-            unsigned long long word = seg_status(epoch, kSegFlagPrefix, 0);  // before block 0: an empty prefix
-            if (at >= 0) word = st[at];
-            const bool valid = (unsigned int)(word >> 35) == (epoch & 0x1fffffffu) && ((word >> 33) & 3ull) != 0ull;
-            const bool is_prefix = valid && ((word >> 33) & 3ull) == kSegFlagPrefix;
-            const uint32_t bp = __ballot_sync(0xffffffffu, is_prefix), binv = __ballot_sync(0xffffffffu, !valid);
-            const int first_p = bp ? __ffs(bp) - 1 : 32;
-            const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
-            if (binv & need) {  // a block this step depends on has not published yet
-                __nanosleep(32);
-                continue;
-            }
-            unsigned long long v = (lane <= first_p) ? (word & 0x1ffffffffull) : 0ull;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            excl += __shfl_sync(0xffffffffu, v, 0);
-            if (first_p < 32) break;
-            look -= 32;
-        }
-        if (lane == 0) {
-            if (bid != 0) {
-                st[bid] = seg_status(epoch, kSegFlagPrefix, excl + block_total);
-                __threadfence();
-            }
-            s_excl = excl;
-            if (bid + 1 == n_blocks) *total_out = excl + block_total;
-        }
-    }
-    __syncthreads();
     // (output positions fit 32 bits: the host side rejects cloths with 2^32 or more possible sticks)
-    unsigned int run = (unsigned int)s_excl;
-    for (int k = 0; k < w; ++k) run += warp_tot[k];
-    const unsigned int cap32 = (unsigned int)min(cap, 0xffffffffull);
-    const unsigned int run0 = run, hl_shift = run0 & 15u;  // (hl itself is 16-byte aligned)
-    unsigned int hl_at = hl_shift;                         // where this trip's highlight bytes go in s_hl[w]
-
-#pragma unroll 1
-    for (int trip = 0; trip < kTrips; ++trip) {
-        if (trip * 32 >= n_here) break;  // warp-uniform
-#if SEG_PREFETCH2
-        Trip nxt = ahead;
-        if (trip + 2 < kTrips) ahead = fetch(trip + 2);
-#else
-        Trip nxt = cur;
-        if (trip + 1 < kTrips) nxt = fetch(trip + 1);  // its loads are in flight while this trip is written out
-#endif
-        const bool v = (cur.fl3 & kV) != 0, h = (cur.fl3 & kH) != 0;
-        const uint32_t bv = __ballot_sync(0xffffffffu, v), bh = __ballot_sync(0xffffffffu, h);
-        const unsigned int total = __popc(bv) + __popc(bh);
-        if (total) {  // warp-uniform
-            const float x2 = (float)cur.x, y2 = (float)cur.y;  // cloth.go:110-111: float32(c.p2.x)
-            // head of the horizontal stick = the lane to the left (lane 0: loaded separately)
-            float xl = __shfl_up_sync(0xffffffffu, x2, 1), yl = __shfl_up_sync(0xffffffffu, y2, 1);
-            if (lane == 0) xl = (float)cur.xl0, yl = (float)cur.yl0;
-            const uint32_t hl_own = cur.fl3 & CLOTHGPU_FLAG_HIGHLIGHT;
-#if SEG_FULL_FAST
-            if ((bv & bh) == 0xffffffffu && run + 64u <= cap32) {
-                // every lane lists both of its sticks (an intact piece of cloth: nearly every trip): lane l's pair goes to
-                // run + 2l, run + 2l + 1 — no ranking, no staging, each lane stores 32 (64) contiguous bytes
-                const unsigned int o = run + 2u * lane;
-                const float4 sv = make_float4((float)cur.xu, (float)cur.yu, x2, y2), sh = make_float4(xl, yl, x2, y2);
-                s_hl[w][hl_at + 2u * lane] = (hl_own & (cur.fl3 >> 8)) != 0;
-                s_hl[w][hl_at + 2u * lane + 1u] = (hl_own & (cur.fl3 >> 16)) != 0;
-                if (QUADS) {
-                    float4 q0, q1, q2, q3;
-                    segment_quad(sv, line_width, q0, q1);
-                    segment_quad(sh, line_width, q2, q3);
-                    out[2ull * o] = q0, out[2ull * o + 1] = q1, out[2ull * o + 2] = q2, out[2ull * o + 3] = q3;
-                } else {
-                    out[o] = sv, out[o + 1] = sh;
-                    if (idx) idx[o] = make_uint2(cur.tail - g.nx, cur.tail), idx[o + 1] = make_uint2(cur.tail - 1, cur.tail);
-                }
-                run += 64u, hl_at += 64u;
-                cur = nxt;
-                continue;
-            }
-#endif
-            unsigned int r = __popc(bv & below) + __popc(bh & below);  // lane l's sticks come after those of lanes < l
-            if (v) {
-                s_xy[w][r] = make_float4((float)cur.xu, (float)cur.yu, x2, y2);
-                s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 8)) != 0;  // cloth.go:127-128: both ends highlighted
-                if (!QUADS) s_idx[w][r] = make_uint2(cur.tail - g.nx, cur.tail);
-                ++r;
-            }
-            if (h) {
-                s_xy[w][r] = make_float4(xl, yl, x2, y2);
-                s_hl[w][hl_at + r] = (hl_own & (cur.fl3 >> 16)) != 0;
-                if (!QUADS) s_idx[w][r] = make_uint2(cur.tail - 1, cur.tail);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const unsigned int j = q * 32 + lane, o = run + j;
-                if (j < total && o < cap32) {
-                    if (QUADS) {
-                        float4 q0, q1;
-                        segment_quad(s_xy[w][j], line_width, q0, q1);
-                        out[2ull * o] = q0, out[2ull * o + 1] = q1;
-                    } else {
-                        out[o] = s_xy[w][j];
-                        if (idx) idx[o] = s_idx[w][j];
-                    }
+    unsigned int run0 = 0;
+    if (plan) {  // block-uniform
+        run0 = __ldg(starts + bid);
+        mbar_wait(&s_bar_plan, 0);
+    } else {
+        // a cloth of a few tiles (the GUI's): no plan launch — the block plans its own tile and counts the tiles before it
+        const uint8_t* fl = P.fl + base;
+        unsigned int* const warp_sums = reinterpret_cast<unsigned int*>(s_xy);
+        for (unsigned int t = 0; t <= bid; ++t) {
+            uint32_t mv, mh, hv, hh;
+            unsigned int all;
+            const unsigned int before = block_exclusive_scan<kSegThreads>(
+                seg_masks16(seg_load16(fl, g, (unsigned int)n, t * (unsigned int)kSegBlock + threadIdx.x * 16u), mv, mh, hv, hh), warp_sums, all);
+            if (t < bid) {
+                run0 += all & kSegCountMask;
+            } else {
+                s_plan.mv[threadIdx.x] = (uint16_t)mv, s_plan.mh[threadIdx.x] = (uint16_t)mh;
+                s_plan.hv[threadIdx.x] = (uint16_t)hv, s_plan.hh[threadIdx.x] = (uint16_t)hh;
+                s_plan.pre[threadIdx.x] = (uint16_t)(before & kSegCountMask);
+                if (threadIdx.x == 0) {
+                    s_plan.total = all & kSegCountMask, s_plan.any_hl = all >> 20;
+                    if (bid + 1u == n_tiles) *total_out = (unsigned long long)run0 + (all & kSegCountMask);
                 }
             }
-            __syncwarp();  // the staging buffer is rewritten by the next trip
-            run += total, hl_at += total;
+            __syncthreads();
         }
-        cur = nxt;
     }
-    // ---- highlight bytes [run0, run) of this warp: whole 16-byte groups as one store, the ragged ends byte by byte ----
-    __syncwarp();
-    const unsigned int first16 = run0 - hl_shift;  // 16-aligned output position of s_hl[w][0]
-    for (unsigned int c = lane * 16u; c < hl_at; c += 32u * 16u) {
-        const unsigned int o = first16 + c;
-        if (c >= hl_shift && c + 16u <= hl_at && o + 16u <= cap32) {
-            *reinterpret_cast<uint4*>(hl + o) = *reinterpret_cast<const uint4*>(&s_hl[w][c]);
-        } else {
-            for (unsigned int b = 0; b < 16u; ++b)
-                if (c + b >= hl_shift && c + b < hl_at && o + b < cap32) hl[o + b] = s_hl[w][c + b];
+    const unsigned int hl_shift = run0 & 15u;  // (hl itself is 16-byte aligned)
+    const unsigned int cap32 = (unsigned int)min(cap, 0xffffffffull);
+    const uint32_t below = (1u << lane) - 1u;
+    const bool any_hl = s_plan.any_hl != 0u;  // block-uniform
+    if (any_hl) {
+        for (int c = threadIdx.x * 16; c < 2 * kSegBlock + 16; c += kSegThreads * 16) *reinterpret_cast<uint4*>(&s_hl[c]) = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+    }
+    const uint32_t* tv = reinterpret_cast<const uint32_t*>(s_plan.mv);
+    const uint32_t* th = reinterpret_cast<const uint32_t*>(s_plan.mh);
+
+    // ---- trips --------------------------------------------------------------------------------------------------------------
+    auto do_trip = [&](const int k, const T* buf) {  // chunk k of the tile, its coordinates at buf[plane * kSegStageN + lane]
+        const uint32_t bv = tv[k], bh = th[k];
+        const unsigned int total = __popc(bv) + __popc(bh);
+        const float x2 = (float)buf[lane], y2 = (float)buf[kSegStageN + lane];  // cloth.go:110-111: float32(c.p2.x)
+        // head of the horizontal stick = the lane to the left (lane 0: the last lane of the chunk before)
+        float xl = __shfl_up_sync(0xffffffffu, x2, 1), yl = __shfl_up_sync(0xffffffffu, y2, 1);
+        if (lane == 0) xl = carry_x, yl = carry_y;
+        carry_x = __shfl_sync(0xffffffffu, x2, 31), carry_y = __shfl_sync(0xffffffffu, y2, 31);
+        if (total == 0) return;  // warp-uniform
+        const unsigned int rel = s_plan.pre[2 * k];  // the chunk's place in the tile's part of the list
+        const unsigned int run = run0 + rel, hl_at = hl_shift + rel;
+        float xu = 0.f, yu = 0.f;
+        if ((bv >> lane) & 1u) xu = (float)buf[2 * kSegStageN + lane], yu = (float)buf[3 * kSegStageN + lane];
+        uint32_t bhv = 0, bhh = 0;
+        if (any_hl) bhv = reinterpret_cast<const uint32_t*>(s_plan.hv)[k], bhh = reinterpret_cast<const uint32_t*>(s_plan.hh)[k];
+        unsigned int tail = 0;  // index of the lane's particle in the (unpadded) cloth: only the index list needs it
+        if (IDX) {
+            const long long p = tile_first + k * 32 + lane;
+            const int row = (int)(p / pitch);
+            tail = (unsigned int)row * (unsigned int)g.nx + (unsigned int)(p - (long long)row * pitch);
         }
+#if SEG_FULL_FAST
+        if ((bv & bh) == 0xffffffffu && run + 64u <= cap32) {
+            // every lane lists both of its sticks: lane l's pair goes to run + 2l, run + 2l + 1 — no ranking, no staging,
+            // each lane stores 32 (64) contiguous bytes
+            const unsigned int o = run + 2u * lane;
+            const float4 sv = make_float4(xu, yu, x2, y2), sh = make_float4(xl, yl, x2, y2);
+            if (bhv | bhh) s_hl[hl_at + 2u * lane] = (bhv >> lane) & 1u, s_hl[hl_at + 2u * lane + 1u] = (bhh >> lane) & 1u;
+            if (QUADS) {
+                float4 q0, q1, q2, q3;
+                segment_quad(sv, line_width, q0, q1);
+                segment_quad(sh, line_width, q2, q3);
+                out[2ull * o] = q0, out[2ull * o + 1] = q1, out[2ull * o + 2] = q2, out[2ull * o + 3] = q3;
+            } else {
+                out[o] = sv, out[o + 1] = sh;
+                if (IDX) idx[o] = make_uint2(tail - g.nx, tail), idx[o + 1] = make_uint2(tail - 1, tail);
+            }
+            return;
+        }
+#endif
+        const bool v = (bv >> lane) & 1u, h = (bh >> lane) & 1u;
+        unsigned int r = __popc(bv & below) + __popc(bh & below);  // lane l's sticks come after those of lanes < l
+        if (v) {
+            s_xy[w][r] = make_float4(xu, yu, x2, y2);
+            if ((bhv >> lane) & 1u) s_hl[hl_at + r] = 1;
+            if (IDX) s_idx[w][r] = make_uint2(tail - g.nx, tail);
+            ++r;
+        }
+        if (h) {
+            s_xy[w][r] = make_float4(xl, yl, x2, y2);
+            if ((bhh >> lane) & 1u) s_hl[hl_at + r] = 1;
+            if (IDX) s_idx[w][r] = make_uint2(tail - 1, tail);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned int j = q * 32 + lane, o = run + j;
+            if (j < total && o < cap32) {
+                if (QUADS) {
+                    float4 q0, q1;
+                    segment_quad(s_xy[w][j], line_width, q0, q1);
+                    out[2ull * o] = q0, out[2ull * o + 1] = q1;
+                } else {
+                    out[o] = s_xy[w][j];
+                    if (IDX) idx[o] = s_idx[w][j];
+                }
+            }
+        }
+        __syncwarp();  // the staging buffer is rewritten by the next trip
+    };
+#pragma unroll 1
+    for (int f = 0; f < kFills; ++f) {
+        if (fill_count(f) <= 0) break;  // warp-uniform
+        const int d = f % kSegStages;
+        mbar_wait(&s_bar[w][d], (unsigned)(f / kSegStages) & 1u);  // the buffer's coordinates have landed
+        if (f == 0) carry_x = (float)carry_tx, carry_y = (float)carry_ty;
+        const T* buf = ring + (size_t)d * 4 * kSegStageN;
+#pragma unroll
+        for (int t = 0; t < kTripsPerFill; ++t) do_trip((warp_lo + f * kSegStageN) / 32 + t, buf + 32 * t);
+        __syncwarp();
+        if (lane == 0 && f + kSegStages < kFills) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the reads above precede the refill
+            issue_fill(f + kSegStages);
+        }
+    }
+    // ---- highlight bytes of the tile's sticks: hl[run0, run0 + total) <- s_hl[hl_shift, hl_end), or zeros.  Whole 16-byte
+    // groups as one store each; the ragged first and last group byte by byte, one thread per byte.
+    if (any_hl) __syncthreads();
+    const unsigned int hl_end = hl_shift + s_plan.total;
+    const unsigned int first16 = run0 - hl_shift;  // 16-aligned output position of s_hl[0]
+    const unsigned int body_lo = hl_shift ? 16u : 0u, body_hi = hl_end & ~15u;
+    for (unsigned int c = body_lo + threadIdx.x * 16u; c < body_hi; c += kSegThreads * 16u) {
+        const uint4 v16 = any_hl ? *reinterpret_cast<const uint4*>(&s_hl[c]) : make_uint4(0, 0, 0, 0);
+        if (first16 + c + 16u <= cap32) *reinterpret_cast<uint4*>(hl + first16 + c) = v16;
+        else
+            for (unsigned int b = 0; b < 16u; ++b)
+                if (first16 + c + b < cap32) hl[first16 + c + b] = any_hl ? s_hl[c + b] : (uint8_t)0;
+    }
+    if (threadIdx.x < 32) {
+        // lanes 0..15: the group before body_lo; lanes 16..31: the group from body_hi on (the same group when all the
+        // tile's bytes fall into one: then only the first half writes)
+        const unsigned int c = lane < 16 ? (unsigned int)lane : max(body_hi, body_lo) + (unsigned int)lane - 16u;
+        const bool mine = lane < 16 ? (body_lo != 0u) : (body_hi >= body_lo);
+        if (mine && c >= hl_shift && c < hl_end && first16 + c < cap32) hl[first16 + c] = any_hl ? s_hl[c] : (uint8_t)0;
     }
 }
 

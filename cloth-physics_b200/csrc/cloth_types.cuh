@@ -229,6 +229,31 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Shared-memory mbarrier and the bulk (TMA, no tensor map) global -> shared copy that completes on it.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE;\n\t"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map: a contiguous run of bytes), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+
 // (*particle).update, physics/particle.go:75-181.  `fl` is the particle's flag byte.
 template <typename T>
 __device__ __forceinline__ void particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,

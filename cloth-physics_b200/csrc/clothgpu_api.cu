@@ -131,13 +131,12 @@ struct clothgpu {
     void* small_frames_dev = nullptr;   // folded FrameU per frame of a resident multi-frame launch (cloth_small.cuh)
     void* small_frames_host = nullptr;  // pinned staging for the above
     size_t small_frames_cap = 0;
-    unsigned long long* seg_status = nullptr;  // look-back status word per block of the export kernel (never cleared: epoch-tagged)
-    size_t seg_status_cap = 0;
+    SegPlan* seg_plan = nullptr;               // the export's plan: one record per tile of kSegBlock particles ...
+    unsigned int* seg_starts = nullptr;        // ... and where every tile's sticks start in the list
+    size_t seg_plan_cap = 0;
     void* seg_out = nullptr;                   // per possible stick: 32 B (quads, or endpoints + indices) + 1 highlight byte
     size_t seg_out_cap = 0;
-    unsigned long long* seg_total = nullptr;   // [0] sticks listed by the last export, [1] the export kernel's block ticket
-    unsigned long long seg_ticket_base = 0;    // blocks launched by all exports so far (the ticket only grows)
-    unsigned int seg_epoch = 0;
+    unsigned long long* seg_total = nullptr;   // [0] sticks listed by the last export, [1] (as unsigned int) the plan kernel's count of finished blocks
 };
 
 namespace {
@@ -746,7 +745,8 @@ void free_all(clothgpu* c) {
     cudaFreeHost(c->frames_host);
     cudaFree(c->small_frames_dev);
     cudaFreeHost(c->small_frames_host);
-    cudaFree(c->seg_status);
+    cudaFree(c->seg_plan);
+    cudaFree(c->seg_starts);
     cudaFree(c->seg_out);
     cudaFree(c->seg_total);
     if (c->frames_copied) cudaEventDestroy(c->frames_copied);
@@ -1259,18 +1259,18 @@ int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float
     const Geom& g = c->g;
     const long long n = (long long)g.nx * g.own_rows;
     const long long padded = (long long)g.pitch * g.own_rows;
-    const unsigned blocks = (unsigned)std::max<long long>(1, (padded + kSegBlock - 1) / kSegBlock);
-    if (c->seg_status_cap < blocks) {
-        cudaFree(c->seg_status);
-        c->seg_status = nullptr;
-        c->seg_status_cap = 0;
-        CU_TRY(cudaMalloc((void**)&c->seg_status, (size_t)blocks * sizeof(unsigned long long)));
-        CU_TRY(cudaMemsetAsync(c->seg_status, 0, (size_t)blocks * sizeof(unsigned long long), c->stream));
-        c->seg_status_cap = blocks;
-        c->seg_epoch = 0;
+    const unsigned blocks = (unsigned)std::max<long long>(1, (padded + kSegBlock - 1) / kSegBlock);  // tiles
+    if (c->seg_plan_cap < blocks) {
+        cudaFree(c->seg_plan);
+        cudaFree(c->seg_starts);
+        c->seg_plan = nullptr, c->seg_starts = nullptr;
+        c->seg_plan_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->seg_plan, (size_t)blocks * sizeof(SegPlan)));
+        CU_TRY(cudaMalloc((void**)&c->seg_starts, ((size_t)blocks + 15) / 16 * 16 * sizeof(unsigned int)));
+        c->seg_plan_cap = blocks;
     }
     const size_t max_sticks = (size_t)2 * n;
-    if (max_sticks > 0xffffffffull)  // the look-back and the scatter keep output positions in 32 bits
+    if (max_sticks > 0xffffffffull || padded > 0xffffffffll)  // the plan and the scatter keep positions in 32 bits
         return fail(CLOTHGPU_ERR_INVALID, "live-stick compaction supports cloths of up to 2^31 particles");
     if (c->seg_out_cap < max_sticks) {
         cudaFree(c->seg_out);
@@ -1282,30 +1282,34 @@ int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float
     float4* d_main = (float4*)c->seg_out;
     uint2* d_idx = (uint2*)(d_main + max_sticks);
     uint8_t* d_hl = (uint8_t*)(d_main + 2 * max_sticks);
-    c->seg_epoch = (c->seg_epoch + 1) & 0x1fffffffu;
-    if (c->seg_epoch == 0) {  // the 29-bit epoch wrapped: forget the old status words once
-        CU_TRY(cudaMemsetAsync(c->seg_status, 0, c->seg_status_cap * sizeof(unsigned long long), c->stream));
-        c->seg_epoch = 1;
+    const bool self_plan = blocks <= kSegSelfPlanTiles;  // one launch: the export blocks plan for themselves
+    if (!self_plan) {
+        unsigned int* const d_done = reinterpret_cast<unsigned int*>(c->seg_total + 1);  // zero between exports
+        segment_plan_kernel<<<std::min(blocks, (unsigned)c->sm_count * (unsigned)SEG_PLAN_BLOCKS_PER_SM), kSegThreads, 0, c->stream>>>(c->FL[c->cur_pos], g, cloth, c->seg_plan, c->seg_starts, blocks, d_done,
+                                                                   c->seg_total);
     }
     auto run = [&](auto tag) {
         using T = decltype(tag);
         Planes<T> P = planes<T>(c, c->cur_pos, c->cur_prev);
+        auto go = [&](auto kernel, uint2* d_i) {
+            if (seg_smem_bytes<T>() + 24 * 1024 > 48 * 1024)  // (static + dynamic above the default limit: opt in)
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem_bytes<T>());
+            kernel<<<blocks, kSegThreads, seg_smem_bytes<T>(), c->stream>>>(P, g, cloth, self_plan ? nullptr : c->seg_plan, c->seg_starts, line_width,
+                                                                              d_main, d_hl, d_i, max_sticks, blocks, c->seg_total);
+        };
         if (quads)
-            segment_export_kernel<T, true><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_status, c->seg_total + 1, c->seg_ticket_base,
-                                                                                     c->seg_epoch, blocks, line_width, d_main, d_hl, nullptr,
-                                                                                     max_sticks, c->seg_total);
+            go(segment_export_kernel<T, true, false>, nullptr);
+        else if (with_idx)
+            go(segment_export_kernel<T, false, true>, d_idx);
         else
-            segment_export_kernel<T, false><<<blocks, kStreamThreads, 0, c->stream>>>(P, g, cloth, c->seg_status, c->seg_total + 1, c->seg_ticket_base,
-                                                                                      c->seg_epoch, blocks, 0.f, d_main, d_hl, with_idx ? d_idx : nullptr,
-                                                                                      max_sticks, c->seg_total);
+            go(segment_export_kernel<T, false, false>, nullptr);
     };
     if (c->precision == CLOTHGPU_F32)
         run(float{});
     else
         run(double{});
     CU_TRY(cudaGetLastError());
-    c->seg_ticket_base += blocks;
-    c->launches += 1;
+    c->launches += self_plan ? 1 : 2;
     if (max_sticks_out) *max_sticks_out = max_sticks;
     return CLOTHGPU_OK;
 }

@@ -7,4 +7,4 @@ mkdir -p build/variants
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xptxas -v \
   -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden -ccbin /usr/bin/g++ -shared \
   -o build/variants/$name.so cloth-physics_b200/csrc/clothgpu_api.cu -lcudart "$@" 2> build/variants/$name.ptxas.log
-grep -A2 "wave_frame_kernelIdLb0ELb0" build/variants/$name.ptxas.log | grep -E "registers|spill" | tr '\n' ' '; echo " [$name]"
+grep -A2 "${PTXAS_KERNEL:-wave_frame_kernelIdLb0ELb0}" build/variants/$name.ptxas.log | grep -E "registers|spill" | tr '\n' ' '; echo " [$name]"
