@@ -216,6 +216,31 @@ def test_live_stick_list_on_random_states(nx, ny, ens):
         assert np.array_equal(w2, want) and np.array_equal(h2, want_hl)
 
 
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 50), (5000, 1), (64, 64), (128, 128), (128, 129), (4096, 4100)])
+def test_live_stick_list_at_the_tile_boundaries_of_the_export(nx, ny):
+    """The export works on tiles of 4096 padded particles: a single particle, one column (15 of 16 padded columns are
+    empty), one row, exactly 1 and exactly 4 tiles (the largest cloth whose export blocks plan for themselves, ONE launch),
+    5 tiles with a ragged last one (the smallest with a plan launch), and more than 4096 tiles (the last plan block scans
+    the tile totals in more than one step).  Highlights only in a few places, then nowhere: most tiles write their
+    highlight bytes as plain zeros, and a second export must not leave the first one's bytes behind."""
+    g = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE))
+    x, y, px, py, fl = random_state(nx, ny, seed=nx + 7 * ny, kill=0.02, holes=0.01)
+    rng = np.random.default_rng(nx * 31 + ny)
+    fl2 = fl.copy()
+    hot = rng.integers(0, fl.size, size=max(1, fl.size // 5000))   # a handful of highlighted spots ...
+    for d in (0, 1, nx):                                           # ... each with its right and lower neighbour
+        fl2[np.minimum(hot + d, fl.size - 1)] |= FLAG_HIGHLIGHT
+    for flags in (fl2, fl & ~np.uint8(FLAG_HIGHLIGHT)):
+        g.write_state(x, y, px, py, flags)
+        st = g.read_state()
+        want, want_hl = _expected_segments_fast(nx, ny, st[0], st[1], st[4])
+        got, got_hl = g.read_segments()
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(got_hl, want_hl)
+        assert g.count_segments() == len(want)
+    assert not want_hl.any()
+
+
 def test_live_stick_lists_of_two_strips_concatenate_to_the_whole_cloth():
     """A strip lists the sticks whose TAIL it owns; the vertical sticks of its first row hang from the ghost row above."""
     nx, ny, split = 333, 80, 34
@@ -257,6 +282,20 @@ def test_outline_quads_match_addsegment_of_the_reference(oracle):
     assert np.array_equal(q2.view(np.uint32), oracle.segment_quads(s2, 0.6).view(np.uint32))
     k = int(np.flatnonzero((s2[:, 0] == s2[:, 2]) & (s2[:, 1] == s2[:, 3]))[0])
     assert np.array_equal(q2[k], np.tile(s2[k, :2], 4))
+
+
+@pytest.mark.parametrize("nx,ny", [(700, 90), (1037, 300)])
+def test_outline_quads_of_a_cloth_of_many_tiles(oracle, nx, ny):
+    """The QUADS instantiation of the export kernel behind a plan launch (more than 4 tiles): random dead sticks, holes and
+    highlights, so both the direct-store and the ranked path run."""
+    g = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE))
+    x, y, px, py, fl = random_state(nx, ny, seed=nx - ny, kill=0.05, holes=0.02)
+    fl[np.random.default_rng(ny).random(fl.size) < 0.1] |= FLAG_HIGHLIGHT
+    g.write_state(x, y, px, py, fl)
+    segs, seg_hl = g.read_segments()
+    quads, hl = g.read_quads(line_width=0.6)
+    assert quads.shape == (len(segs), 8) and np.array_equal(hl, seg_hl)
+    assert np.array_equal(quads.view(np.uint32), oracle.segment_quads(segs, 0.6).view(np.uint32))
 
 
 @pytest.mark.parametrize("K,schedule", [(8, SCHED_FUSED), (8, SCHED_WAVE), (1, SCHED_FUSED), (1, SCHED_ROWSTREAM)])
