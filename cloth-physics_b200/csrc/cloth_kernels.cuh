@@ -421,6 +421,14 @@ __device__ __forceinline__ void segment_quad(const float4 s, float line_width, f
     q1 = make_float4(s.z - nx, s.w - ny, s.x - nx, s.y - ny);
 }
 
+// 32 contiguous, 32-byte aligned bytes in ONE store (sm_100: 256-bit global stores): a whole sector per lane, whether
+// the list lives in HBM or — written directly by the kernel — in pinned host memory.
+__device__ __forceinline__ void st_pair(float4* p, const float4& a, const float4& b) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+                 "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+
 // One block per tile.  The plan arrives by one bulk copy; every warp owns 512 consecutive particles (16 chunks) and a
 // private ring of kSegStages buffers in shared memory, each holding x, y of kSegStageN consecutive particles and of the
 // kSegStageN above them, which one lane hands to the TMA engine — four bulk copies per buffer, completing on the buffer's
@@ -587,9 +595,10 @@ __global__ void __launch_bounds__(kSegThreads, SEG_MIN_BLOCKS)
                 float4 q0, q1, q2, q3;
                 segment_quad(sv, line_width, q0, q1);
                 segment_quad(sh, line_width, q2, q3);
-                out[2ull * o] = q0, out[2ull * o + 1] = q1, out[2ull * o + 2] = q2, out[2ull * o + 3] = q3;
+                st_pair(out + 2ull * o, q0, q1), st_pair(out + 2ull * o + 2, q2, q3);
             } else {
-                out[o] = sv, out[o + 1] = sh;
+                if (run & 1u) out[o] = sv, out[o + 1] = sh;  // (warp-uniform)
+                else st_pair(out + o, sv, sh);
                 if (IDX) idx[o] = make_uint2(tail - g.nx, tail), idx[o + 1] = make_uint2(tail - 1, tail);
             }
             return;
@@ -616,7 +625,7 @@ __global__ void __launch_bounds__(kSegThreads, SEG_MIN_BLOCKS)
                 if (QUADS) {
                     float4 q0, q1;
                     segment_quad(s_xy[w][j], line_width, q0, q1);
-                    out[2ull * o] = q0, out[2ull * o + 1] = q1;
+                    st_pair(out + 2ull * o, q0, q1);
                 } else {
                     out[o] = s_xy[w][j];
                     if (IDX) idx[o] = s_idx[w][j];

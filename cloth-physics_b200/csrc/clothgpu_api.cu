@@ -131,6 +131,7 @@ struct clothgpu {
     void* small_frames_dev = nullptr;   // folded FrameU per frame of a resident multi-frame launch (cloth_small.cuh)
     void* small_frames_host = nullptr;  // pinned staging for the above
     size_t small_frames_cap = 0;
+    bool direct_export = true;                 // small exports into pinned caller memory: written by the kernel, no copies (CLOTHGPU_DIRECT_EXPORT=0: off)
     SegPlan* seg_plan = nullptr;               // the export's plan: one record per tile of kSegBlock particles ...
     unsigned int* seg_starts = nullptr;        // ... and where every tile's sticks start in the list
     size_t seg_plan_cap = 0;
@@ -879,6 +880,7 @@ int clothgpu_create(const clothgpu_desc* desc, clothgpu** out) {
         c->s1_ring = atoi(s);
         c->s1_warps_per_sm = c->s1_ring == 2 ? 4 * S1_RING_CTAS : 4 * S1_MIN_CTAS;  // (3 stages: 48 KB per CTA, 4 CTAs fit)
     }
+    if (const char* s = getenv("CLOTHGPU_DIRECT_EXPORT")) c->direct_export = atoi(s) != 0;
     if (const char* s = getenv("CLOTHGPU_S1_WARPS")) c->s1_warps_per_sm = std::max(1, atoi(s));
     if (const char* s = getenv("CLOTHGPU_SWEEPS_PER_LAUNCH")) {
         const int v = atoi(s);
@@ -1254,7 +1256,17 @@ namespace {
 // Live-stick export on the handle's stream: ONE launch (per-block counts, decoupled look-back, ballot-ranked scatter) into
 // c->seg_out.  quads = false: float4 endpoints at [0, n), optional uint2 indices behind them; quads = true: 2 float4 of
 // outline per stick.  Highlight bytes behind the 32 B/stick area in both cases.
-int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float line_width, size_t* max_sticks_out) {
+// Where an export goes when not into the handle's own device buffer: device-visible addresses of the caller's pinned host
+// memory (null = the handle's buffer), the list's capacity there, and where its length is to be written.
+struct ExportTarget {
+    float4* main = nullptr;
+    uint8_t* hl = nullptr;
+    uint2* idx = nullptr;
+    unsigned long long* total = nullptr;
+    size_t cap = 0;
+};
+int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float line_width, size_t* max_sticks_out,
+                    const ExportTarget* direct = nullptr) {
     if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
     const Geom& g = c->g;
     const long long n = (long long)g.nx * g.own_rows;
@@ -1282,11 +1294,19 @@ int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float
     float4* d_main = (float4*)c->seg_out;
     uint2* d_idx = (uint2*)(d_main + max_sticks);
     uint8_t* d_hl = (uint8_t*)(d_main + 2 * max_sticks);
+    unsigned long long* d_total = c->seg_total;
+    size_t list_cap = max_sticks;
+    if (direct) {  // the kernel writes the caller's pinned memory itself
+        if (direct->main) d_main = direct->main;
+        if (direct->hl) d_hl = direct->hl;
+        if (direct->idx) d_idx = direct->idx;
+        d_total = direct->total, list_cap = direct->cap;
+    }
     const bool self_plan = blocks <= kSegSelfPlanTiles;  // one launch: the export blocks plan for themselves
     if (!self_plan) {
         unsigned int* const d_done = reinterpret_cast<unsigned int*>(c->seg_total + 1);  // zero between exports
         segment_plan_kernel<<<std::min(blocks, (unsigned)c->sm_count * (unsigned)SEG_PLAN_BLOCKS_PER_SM), kSegThreads, 0, c->stream>>>(c->FL[c->cur_pos], g, cloth, c->seg_plan, c->seg_starts, blocks, d_done,
-                                                                   c->seg_total);
+                                                                   d_total);
     }
     auto run = [&](auto tag) {
         using T = decltype(tag);
@@ -1295,7 +1315,7 @@ int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float
             if (seg_smem_bytes<T>() + 24 * 1024 > 48 * 1024)  // (static + dynamic above the default limit: opt in)
                 cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem_bytes<T>());
             kernel<<<blocks, kSegThreads, seg_smem_bytes<T>(), c->stream>>>(P, g, cloth, self_plan ? nullptr : c->seg_plan, c->seg_starts, line_width,
-                                                                              d_main, d_hl, d_i, max_sticks, blocks, c->seg_total);
+                                                                              d_main, d_hl, d_i, list_cap, blocks, d_total);
         };
         if (quads)
             go(segment_export_kernel<T, true, false>, nullptr);
@@ -1316,6 +1336,39 @@ int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float
 
 // Copy an export back.  Small lists (GUI-sized cloths) are copied at the caller's full capacity together with the count
 // and synchronised once — the count is then only checked afterwards; large ones wait for the count and copy exactly n.
+// GUI-sized lists skip the copies altogether when the caller's buffers are pinned host memory: the export kernel stores
+// straight into them over PCIe (32-byte stores) and writes the list's length next to the counters; one synchronisation.
+// Returns false when the buffers do not qualify (pageable memory, alignment, a list too long to be worth it).
+constexpr size_t kDirectExportBytes = (size_t)2 << 20;
+bool direct_target(clothgpu* c, void* main_dst, void* hl_dst, void* idx_dst, size_t cap, size_t max_sticks, ExportTarget* out) {
+    if (!main_dst || !c->direct_export) return false;
+    if (std::min(cap, max_sticks) * 33 > kDirectExportBytes) return false;
+    auto device_view = [](void* host, size_t align, void** dev) {
+        if (!host) return true;  // (not wanted: the kernel writes the handle's own buffer instead)
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        if (at.type != cudaMemoryTypeHost || !at.devicePointer || ((uintptr_t)at.devicePointer % align)) return false;
+        *dev = at.devicePointer;
+        return true;
+    };
+    void *m = nullptr, *h = nullptr, *i = nullptr;
+    if (!device_view(main_dst, 32, &m) || !device_view(hl_dst, 16, &h) || !device_view(idx_dst, 8, &i)) return false;
+    out->main = (float4*)m, out->hl = (uint8_t*)h, out->idx = (uint2*)i;
+    out->total = (unsigned long long*)(c->ctr_host + 2 * sizeof(DevCounters) + 5 * sizeof(unsigned long long));  // (pinned: one address on both sides)
+    out->cap = cap;
+    return true;
+}
+int finish_direct(clothgpu* c, size_t cap, size_t* n_out) {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned long long total = *(unsigned long long*)(c->ctr_host + 2 * sizeof(DevCounters) + 5 * sizeof(unsigned long long));
+    *n_out = (size_t)total;
+    if (total > cap) return fail(CLOTHGPU_ERR_CAPACITY, "%llu live sticks, capacity %zu", total, cap);
+    return CLOTHGPU_OK;
+}
+
 struct ExportCopy {
     void* dst;
     const void* src;
@@ -1354,6 +1407,11 @@ int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t*
     if (int rc = check_handle(c)) return rc;
     if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
     size_t max_sticks = 0;
+    ExportTarget direct;
+    if (direct_target(c, xyxy, highlighted, sticks_idx, cap, (size_t)2 * c->g.nx * c->g.own_rows, &direct)) {
+        if (int rc = compact_enqueue(c, cloth, sticks_idx != nullptr, false, 0.f, &max_sticks, &direct)) return rc;
+        return finish_direct(c, cap, n_out);
+    }
     if (int rc = compact_enqueue(c, cloth, sticks_idx != nullptr, false, 0.f, &max_sticks)) return rc;
     float4* d_main = (float4*)c->seg_out;
     const ExportCopy copies[3] = {{xyxy, d_main, sizeof(float4)},
@@ -1368,6 +1426,11 @@ int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float*
     if (!n_out) return fail(CLOTHGPU_ERR_INVALID, "null n");
     if (!(line_width >= 0.f) || !(line_width <= 1e30f)) return fail(CLOTHGPU_ERR_INVALID, "line width must be finite and >= 0");
     size_t max_sticks = 0;
+    ExportTarget direct;
+    if (direct_target(c, quads, highlighted, nullptr, cap, (size_t)2 * c->g.nx * c->g.own_rows, &direct)) {
+        if (int rc = compact_enqueue(c, cloth, false, true, line_width, &max_sticks, &direct)) return rc;
+        return finish_direct(c, cap, n_out);
+    }
     if (int rc = compact_enqueue(c, cloth, false, true, line_width, &max_sticks)) return rc;
     float4* d_main = (float4*)c->seg_out;
     const ExportCopy copies[2] = {{quads, d_main, 2 * sizeof(float4)}, {highlighted, (uint8_t*)(d_main + 2 * max_sticks), 1}};

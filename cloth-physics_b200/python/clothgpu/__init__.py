@@ -238,6 +238,13 @@ class Cloth:
                                                C.cast(hl_ptr, C.POINTER(C.c_uint8)), cap, C.byref(n)))
         return n.value
 
+    def read_segments_into(self, seg_ptr, hl_ptr, idx_ptr, cap, cloth=0):
+        """clothgpu_read_segments_f32 into caller-owned (e.g. pinned) host memory given as raw addresses (0 = not wanted)."""
+        n = C.c_size_t(0)
+        _check(self._L.clothgpu_read_segments_f32(self._h, cloth, C.cast(seg_ptr, C.POINTER(C.c_float)), C.cast(hl_ptr, C.POINTER(C.c_uint8)),
+                                                  C.cast(idx_ptr, C.POINTER(C.c_uint32)), cap, C.byref(n)))
+        return n.value
+
     def compact_segments(self, cloth=0):
         """Device-side live-stick compaction only (asynchronous)."""
         _check(self._L.clothgpu_compact_segments(self._h, cloth))

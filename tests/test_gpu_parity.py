@@ -284,6 +284,47 @@ def test_outline_quads_match_addsegment_of_the_reference(oracle):
     assert np.array_equal(q2[k], np.tile(s2[k, :2], 4))
 
 
+@pytest.mark.parametrize("nx,ny", [(171, 36), (150, 100), (2, 9)])
+def test_export_written_straight_into_pinned_host_memory(nx, ny):
+    """GUI-sized lists: when the caller's buffers are pinned host memory the export kernel stores into them itself (no
+    device buffer, no copies).  Same bytes as the copy path that pageable buffers take; buffers that do not qualify
+    (misaligned, one of them pageable) fall back silently; a list longer than the capacity is an error, and nothing is
+    written behind the capacity."""
+    import torch
+    g = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE))
+    x, y, px, py, fl = random_state(nx, ny, seed=nx * ny, kill=0.05, holes=0.02)
+    fl[np.random.default_rng(nx).random(fl.size) < 0.2] |= FLAG_HIGHLIGHT
+    g.write_state(x, y, px, py, fl)
+    segs, hl, idx = g.read_segments(with_indices=True)      # pageable numpy buffers: the copy path
+    quads, qhl = g.read_quads(line_width=0.6)
+    n, cap = len(segs), 2 * nx * ny
+    pin = lambda shape, dt: torch.full(shape, 77, dtype=dt).pin_memory()
+    ps, ph, pi, pq = pin((cap + 2, 4), torch.float32), pin((cap + 32,), torch.uint8), pin((cap, 2), torch.int32), pin((cap + 2, 8), torch.float32)
+    assert g.read_segments_into(ps.data_ptr(), ph.data_ptr(), pi.data_ptr(), cap) == n
+    assert np.array_equal(ps.numpy()[:n].view(np.uint32), segs.view(np.uint32)) and np.array_equal(ph.numpy()[:n], hl)
+    assert np.array_equal(pi.numpy()[:n].view(np.uint32), idx.view(np.uint32))
+    assert (ps.numpy()[n:] == 77).all() and (ph.numpy()[n:] == 77).all()      # nothing behind the list
+    assert g.read_quads_into(pq.data_ptr(), ph.data_ptr(), cap) == n
+    assert np.array_equal(pq.numpy()[:n].view(np.uint32), quads.view(np.uint32)) and np.array_equal(ph.numpy()[:n], qhl)
+    # without the highlight bytes / the indices
+    ps.fill_(77)
+    assert g.read_segments_into(ps.data_ptr(), 0, 0, cap) == n
+    assert np.array_equal(ps.numpy()[:n].view(np.uint32), segs.view(np.uint32))
+    # a destination that is not 32-byte aligned, a highlight buffer that is not 16-byte aligned: the copy path, same result
+    ps.fill_(77), ph.fill_(77)
+    assert g.read_segments_into(ps.data_ptr() + 16, ph.data_ptr() + 3, 0, cap) == n
+    assert np.array_equal(ps.numpy().ravel()[4:4 + 4 * n].view(np.uint32), segs.ravel().view(np.uint32))
+    assert np.array_equal(ph.numpy()[3:3 + n], hl)
+    # capacity below the list's length
+    if n > 40:
+        ps.fill_(77), ph.fill_(77)
+        small = n - 33
+        with pytest.raises(clothgpu.ClothGpuError):
+            g.read_segments_into(ps.data_ptr(), ph.data_ptr(), 0, small)
+        assert (ps.numpy()[small:] == 77).all() and (ph.numpy()[small:] == 77).all()
+        assert np.array_equal(ps.numpy()[:small].view(np.uint32), segs[:small].view(np.uint32))
+
+
 @pytest.mark.parametrize("nx,ny", [(700, 90), (1037, 300)])
 def test_outline_quads_of_a_cloth_of_many_tiles(oracle, nx, ny):
     """The QUADS instantiation of the export kernel behind a plan launch (more than 4 tiles): random dead sticks, holes and
