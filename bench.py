@@ -524,7 +524,7 @@ def e2e_render(ctx, arm, steps, start):
     ms = sorted(blocks)[len(blocks) // 2]
     return {"ms_per_frame": ms / steps, "frames_per_s": steps / (ms * 1e-3), "h2d_bytes_per_step": C.sizeof(arm.abi.Frame),
             "d2h_bytes_per_step": int(state["n"]) * 33 + 8, "live_sticks": int(state["n"]), "blocks": len(blocks),
-            "what": "clothgpu_step(host frame) + clothgpu_read_quads_f32 into pinned host memory (32 B of outline quad + 1 highlight byte per live stick) per frame"}
+            "what": "clothgpu_step(host frame) + clothgpu_read_quads_f32 into pinned host memory (32 B of outline quad + 1 highlight byte per live stick) per frame; lists of at most 2 MB are stored there by the export kernel itself, longer ones copied"}
 
 
 def strip_parity(ctx):
