@@ -1420,6 +1420,27 @@ int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* xyxy, uint8_t*
     return copy_export(c, max_sticks, cap, copies, 3, n_out);
 }
 
+int clothgpu_host_alloc(size_t bytes, void** p) {
+    if (!p) return fail(CLOTHGPU_ERR_INVALID, "null p");
+    *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(p, std::max<size_t>(bytes, 1), cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? CLOTHGPU_ERR_NOMEM : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? CLOTHGPU_ERR_NODEVICE : CLOTHGPU_ERR_CUDA,
+                    "cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return CLOTHGPU_OK;
+}
+int clothgpu_host_free(void* p) {
+    if (!p) return CLOTHGPU_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CLOTHGPU_ERR_INVALID, "cudaFreeHost: %s (not memory of clothgpu_host_alloc?)", cudaGetErrorString(e));
+    }
+    return CLOTHGPU_OK;
+}
+
 int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float* quads, uint8_t* highlighted,
                             size_t cap, size_t* n_out) {
     if (int rc = check_handle(c)) return rc;

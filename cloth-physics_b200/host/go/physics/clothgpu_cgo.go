@@ -58,9 +58,11 @@ type Cloth struct {
 	posX      int
 	posY      int
 	frames    uint64
-	// host staging for the render export, reused across frames
-	quads []float32
-	hl    []uint8
+	// host staging for the render export, reused across frames: page-locked memory of clothgpu_host_alloc (the export
+	// kernel stores the GUI cloth's list straight into it — no copies), viewed as Go slices
+	quadsMem, hlMem unsafe.Pointer
+	quads           []float32
+	hl              []uint8
 }
 
 // NewCloth mirrors physics/cloth.go:31-38.  No device work happens until Init.
@@ -115,6 +117,9 @@ func (c *Cloth) Close() {
 		runtime.SetFinalizer(c, nil)
 		C.clothgpu_destroy(c.gpu)
 		c.gpu = nil
+		C.clothgpu_host_free(c.quadsMem)
+		C.clothgpu_host_free(c.hlMem)
+		c.quadsMem, c.hlMem, c.quads, c.hl = nil, nil, nil, nil
 	}
 }
 
@@ -168,8 +173,13 @@ func (c *Cloth) Update(gtx layout.Context, mouse *Mouse, hud *gui.Hud, dt float6
 	var n C.size_t
 	if c.capSticks > 0 { // (a 1 x 1 "cloth" has no sticks: nothing to read back, and &c.quads[0] would panic)
 		if len(c.quads) < 8*c.capSticks {
-			c.quads = make([]float32, 8*c.capSticks)
-			c.hl = make([]uint8, c.capSticks)
+			C.clothgpu_host_free(c.quadsMem)
+			C.clothgpu_host_free(c.hlMem)
+			c.quadsMem, c.hlMem = nil, nil
+			c.check(C.clothgpu_host_alloc(C.size_t(32*c.capSticks), &c.quadsMem))
+			c.check(C.clothgpu_host_alloc(C.size_t(c.capSticks), &c.hlMem))
+			c.quads = unsafe.Slice((*float32)(c.quadsMem), 8*c.capSticks)
+			c.hl = unsafe.Slice((*uint8)(c.hlMem), c.capSticks)
 		}
 		c.check(C.clothgpu_read_quads_f32(c.gpu, 0, C.float(strokeWidth), (*C.float)(unsafe.Pointer(&c.quads[0])),
 			(*C.uint8_t)(unsafe.Pointer(&c.hl[0])), C.size_t(c.capSticks), &n))

@@ -167,6 +167,24 @@ class Cloth {
         return n;
     }
 
+    // Quads into page-locked memory the handle keeps (clothgpu_host_alloc): for GUI-sized cloths the export kernel writes
+    // the list there itself — one launch, one synchronisation, no copies.  The pointers stay valid until Close().
+    size_t QuadsPinned(const float*& quads, const uint8_t*& highlighted, float lineWidth = 0.6f) {
+        clothgpu_info info;
+        Check(clothgpu_get_info(gpu_, &info), "QuadsPinned");
+        const size_t cap = (size_t)info.sticks;
+        if (cap > pinned_cap_) {
+            FreePinned();
+            Check(clothgpu_host_alloc(cap * 32, &pinned_quads_), "QuadsPinned");
+            Check(clothgpu_host_alloc(cap, &pinned_hl_), "QuadsPinned");
+            pinned_cap_ = cap;
+        }
+        size_t n = 0;
+        if (cap) Check(clothgpu_read_quads_f32(gpu_, 0, lineWidth, (float*)pinned_quads_, (uint8_t*)pinned_hl_, cap, &n), "QuadsPinned");
+        quads = (const float*)pinned_quads_, highlighted = (const uint8_t*)pinned_hl_;
+        return n;
+    }
+
     clothgpu_counters Counters() {
         clothgpu_counters c;
         Check(clothgpu_get_counters(gpu_, &c), "Counters");
@@ -176,12 +194,21 @@ class Cloth {
     void Close() {
         if (gpu_) clothgpu_destroy(gpu_);
         gpu_ = nullptr;
+        FreePinned();
     }
 
     clothgpu* Handle() { return gpu_; }
     int Iterations = 1;  // extension: relaxation sweeps per frame (the reference does 1)
 
   private:
+    void FreePinned() {
+        clothgpu_host_free(pinned_quads_);
+        clothgpu_host_free(pinned_hl_);
+        pinned_quads_ = pinned_hl_ = nullptr;
+        pinned_cap_ = 0;
+    }
+    void *pinned_quads_ = nullptr, *pinned_hl_ = nullptr;
+    size_t pinned_cap_ = 0;
     static void Check(int rc, const char* what) {
         if (rc != CLOTHGPU_OK) throw std::runtime_error(std::string(what) + ": " + clothgpu_last_error());
     }

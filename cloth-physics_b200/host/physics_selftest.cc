@@ -49,6 +49,18 @@ int main(int argc, char** argv) {
     for (uint8_t h : hl) nh += h != 0;
     double sum = 0;
     for (const auto& s : seg) sum += (double)s.x1 + s.y1 + s.x2 + s.y2;
+    // the outline quads through pageable vectors (copies) and through the handle's page-locked buffers (written by the
+    // export kernel itself): the same bytes
+    std::vector<float> quads;
+    std::vector<uint8_t> qhl;
+    const size_t nq = cloth->Quads(quads, qhl);
+    const float* pq = nullptr;
+    const uint8_t* ph = nullptr;
+    const size_t np = cloth->QuadsPinned(pq, ph);
+    if (nq != n || np != n || memcmp(pq, quads.data(), n * 32) != 0 || memcmp(ph, qhl.data(), n) != 0 || memcmp(ph, hl.data(), n) != 0) {
+        fprintf(stderr, "pinned and pageable quad lists differ\n");
+        return 1;
+    }
     const clothgpu_counters c = cloth->Counters();
     printf("{\"frames\": %llu, \"live_sticks\": %llu, \"alive_sticks\": %llu, \"inactive\": %llu, \"pinned\": %llu, "
            "\"highlighted\": %llu, \"relaxations\": %llu, \"segments\": %zu, \"highlighted_segments\": %zu, \"segment_sum\": %.17g}\n",

@@ -23,7 +23,8 @@ EXPORTS = [
     "clothgpu_frame_default", "clothgpu_desc_default", "clothgpu_create", "clothgpu_reset",
     "clothgpu_destroy", "clothgpu_step", "clothgpu_step_n", "clothgpu_step_each", "clothgpu_sync",
     "clothgpu_get_info", "clothgpu_set_schedule", "clothgpu_read_state", "clothgpu_write_state",
-    "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_read_quads_f32", "clothgpu_compact_segments",
+    "clothgpu_read_masks", "clothgpu_read_segments_f32", "clothgpu_read_quads_f32", "clothgpu_host_alloc", "clothgpu_host_free",
+    "clothgpu_compact_segments",
     "clothgpu_get_counters",
     "clothgpu_halo_region", "clothgpu_strip_export", "clothgpu_strip_attach", "clothgpu_strip_push", "clothgpu_set_stream", "clothgpu_last_step_ms", "clothgpu_launch_count",
     "clothgpu_last_schedule", "clothgpu_selftest_stickmath", "clothgpu_selftest_stickmath_f32", "clothgpu_save_state", "clothgpu_load_state",
@@ -72,6 +73,9 @@ def lib():
         L.clothgpu_read_quads_f32.argtypes = [vp, C.c_int32, C.c_float, C.POINTER(C.c_float), u8p,
                                               C.c_size_t, C.POINTER(C.c_size_t)]
         L.clothgpu_compact_segments.argtypes = [vp, C.c_int32]
+        if hasattr(L, "clothgpu_host_alloc"):
+            L.clothgpu_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+            L.clothgpu_host_free.argtypes = [C.c_void_p]
         L.clothgpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.clothgpu_halo_region.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.clothgpu_strip_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -122,6 +126,32 @@ def selftest_stickmath_f32(device=0):
     rep = _abi.StickMathReport()
     _check(lib().clothgpu_selftest_stickmath_f32(device, C.byref(rep)))
     return rep.as_dict()
+
+
+class HostBuffer:
+    """Page-locked host memory of clothgpu_host_alloc as a numpy array (the export writes such buffers directly)."""
+
+    def __init__(self, shape, dtype):
+        import numpy as np
+        self._L = lib()
+        self.shape, self.dtype = tuple(np.atleast_1d(shape)), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(self._L.clothgpu_host_alloc(self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(1, self.nbytes)).from_address(self.ptr))[:self.nbytes].view(self.dtype).reshape(self.shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            _check(self._L.clothgpu_host_free(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Cloth:

@@ -266,6 +266,14 @@ CLOTHGPU_API int clothgpu_read_segments_f32(clothgpu* c, int32_t cloth, float* x
 CLOTHGPU_API int clothgpu_read_quads_f32(clothgpu* c, int32_t cloth, float line_width, float* quads,
                             uint8_t* highlighted, size_t cap, size_t* n);
 
+/* Page-locked host memory for the two calls above (32-byte aligned; no reference counterpart — Go slices are pageable).
+ * When `xyxy` / `quads`, `highlighted` and `sticks_idx` all lie in such memory (this allocator's, cudaHostAlloc'ed or
+ * cudaHostRegister'ed) and the list is at most 2 MB, the export kernel stores the list there itself and the call is one
+ * launch and one synchronisation — no device buffer, no copies.  Any other destination works too, through copies.
+ * clothgpu_host_free(NULL) is a no-op. */
+CLOTHGPU_API int clothgpu_host_alloc(size_t bytes, void** p);
+CLOTHGPU_API int clothgpu_host_free(void* p);
+
 /* Only the device half of the above: build the compacted live-stick list of cloth `cloth` in device memory,
  * asynchronously on the handle's stream (the next clothgpu_read_segments_f32 re-runs it; with all three output
  * pointers NULL that call returns just the count).  Lets a renderer that consumes the list on the GPU, or a benchmark

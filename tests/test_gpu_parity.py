@@ -325,6 +325,28 @@ def test_export_written_straight_into_pinned_host_memory(nx, ny):
         assert np.array_equal(ps.numpy()[:small].view(np.uint32), segs[:small].view(np.uint32))
 
 
+def test_host_buffers_of_the_library_take_the_direct_export(oracle):
+    """clothgpu_host_alloc / clothgpu_host_free (what the cgo shim stages its render lists in): the scripted trace's quads
+    through such buffers frame by frame equal the copy path's, and the allocator rejects what it did not allocate."""
+    desc = _abi.default_desc()
+    g, o = make_pair(oracle, desc, _abi.SCHED_AUTO)
+    cap = 2 * 171 * 36
+    q, h = clothgpu.HostBuffer((cap, 8), np.float32), clothgpu.HostBuffer((cap,), np.uint8)
+    assert q.ptr % 32 == 0 and h.ptr % 32 == 0
+    for t, f in enumerate(c0_trace(460)):
+        g.step(f)
+        if t % 23 == 0 or t > 440:
+            n = g.read_quads_into(q.ptr, h.ptr, cap)
+            want, want_hl = g.read_quads()
+            assert n == len(want) and np.array_equal(q.array[:n].view(np.uint32), want.view(np.uint32)) and np.array_equal(h.array[:n], want_hl)
+    segs, _ = g.read_segments()
+    assert np.array_equal(q.array[:n].view(np.uint32), oracle.segment_quads(segs, 0.6).view(np.uint32))
+    q.close(), h.close()
+    q.close()                                            # (idempotent)
+    with pytest.raises(clothgpu.ClothGpuError):
+        clothgpu._check(clothgpu.lib().clothgpu_host_free(np.zeros(8).ctypes.data))
+
+
 @pytest.mark.parametrize("nx,ny", [(700, 90), (1037, 300)])
 def test_outline_quads_of_a_cloth_of_many_tiles(oracle, nx, ny):
     """The QUADS instantiation of the export kernel behind a plan launch (more than 4 tiles): random dead sticks, holes and
