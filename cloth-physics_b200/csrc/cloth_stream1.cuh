@@ -37,6 +37,11 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
+#ifndef S1_UNROLL
+#define S1_UNROLL 1
+#endif
+constexpr int kS1Unroll = S1_UNROLL;  // trips per pass of the row loop (2 removes the register moves of the loop-carried
+                                      // rows but measured 3.93 ms at 96 registers — spills — and 3.37 ms at 120 registers / 4 CTAs, against 3.20 ms)
 
 // What a lane owns of one plane row: 16 bytes = NP (even, odd) column pairs.
 template <typename T>
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         }
     }
     int stage = 0;
-#pragma unroll 1
+#pragma unroll(kS1Unroll)
     for (int r = rs; r < re; r += 2) {
         RowRaw<T> reg0, reg1;  // RING == 0 only: this trip's rows, in registers
         if (RING == 0) {
