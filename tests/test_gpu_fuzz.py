@@ -82,3 +82,59 @@ def test_all_schedules_agree_on_random_cases(seed):
         for e in range(ens):
             assert_same_state(results[sched][e], ref[e], f"seed {seed}: {nx}x{ny} x{ens} K={K} prec={prec} schedule {sched} cloth {e}")
         assert counters[sched] == counters[SCHED_STREAMING], f"seed {seed}: counters of schedule {sched}"
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_live_stick_export_on_random_cases(seed):
+    """Random shapes (1 particle .. several hundred tiles), ensembles, precisions, two strips, and densities of dead sticks,
+    holes and highlights from none to all: segments, highlight bytes, indices and outline quads against numpy /
+    the copy path, through pageable buffers and through pinned ones (written by the kernel itself when small enough)."""
+    import torch
+    from test_gpu_parity import _exchange_halos_same_device, _expected_segments_fast
+    from clothgpu._abi import FLAG_HIGHLIGHT
+    rng = np.random.default_rng(7000 + seed)
+    kind = seed % 4
+    nx, ny = [(int(rng.integers(1, 40)), int(rng.integers(1, 40))), (int(rng.integers(1, 300)), int(rng.integers(1, 200))),
+              (int(rng.integers(200, 1500)), int(rng.integers(100, 900))), (int(rng.integers(1, 9)), int(rng.integers(500, 3000)))][kind]
+    ens = int(rng.integers(1, 4)) if kind < 2 else 1
+    prec = _abi.F32 if seed % 5 == 0 else _abi.F64
+    kill, holes, hot = [float(rng.choice([0.0, 0.02, 0.3, 1.0])) for _ in range(3)]
+    e = int(rng.integers(0, ens))
+    g = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, ensemble=ens, precision=prec))
+    for k in range(ens):
+        st = list(random_state(nx, ny, seed=90 * seed + k, kill=kill, holes=holes))
+        st[4][rng.random(st[4].size) < hot] |= FLAG_HIGHLIGHT
+        if prec == _abi.F32:
+            st[:4] = [a.astype(np.float32).astype(np.float64) for a in st[:4]]
+        g.write_state(*st, cloth=k)
+        if k == e:
+            mine = st
+    x, y, _, _, fl = g.read_state(cloth=e)
+    want, want_hl = _expected_segments_fast(nx, ny, x, y, fl)
+    got, got_hl, idx = g.read_segments(cloth=e, with_indices=True)
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (nx, ny, ens)
+    assert np.array_equal(got_hl, want_hl)
+    n = len(want)
+    if n:
+        d = idx[:, 1].astype(np.int64) - idx[:, 0]
+        assert np.all((d == 1) | (d == nx))
+    quads, qhl = g.read_quads(cloth=e, line_width=0.6)
+    assert len(quads) == n and np.array_equal(qhl, want_hl)
+    cap = max(1, 2 * nx * ny)
+    pq, ph = torch.full((cap, 8), 5.0).pin_memory(), torch.full((cap,), 9, dtype=torch.uint8).pin_memory()
+    assert g.read_quads_into(pq.data_ptr(), ph.data_ptr(), cap, cloth=e) == n
+    assert np.array_equal(pq.numpy()[:n].view(np.uint32), quads.view(np.uint32)) and np.array_equal(ph.numpy()[:n], want_hl)
+    ps = torch.full((cap, 4), 5.0).pin_memory()
+    assert g.read_segments_into(ps.data_ptr(), ph.data_ptr(), 0, cap, cloth=e) == n
+    assert np.array_equal(ps.numpy()[:n].view(np.uint32), want.view(np.uint32))
+    if seed % 3 == 0 and ny > 3 and ens == 1:   # the same cloth as two strips: their lists concatenate to the whole one
+        split = max(2, int(rng.integers(2, ny)) & ~1)   # strips start on an even row
+        up = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=1, precision=prec, strip_row0=0, strip_rows=split))
+        lo = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_NONE, max_iterations=1, precision=prec, strip_row0=split, strip_rows=ny - split))
+        up.write_state(*[a.reshape(ny, nx)[:split].ravel() for a in mine])
+        lo.write_state(*[a.reshape(ny, nx)[split:].ravel() for a in mine])
+        _exchange_halos_same_device(up, lo)
+        su, hu = up.read_segments()
+        sl, hl = lo.read_segments()
+        assert len(su) + len(sl) == n, (nx, ny, split)
+        assert np.array_equal(np.concatenate([su, sl]).view(np.uint32), want.view(np.uint32)) and np.array_equal(np.concatenate([hu, hl]), want_hl)
