@@ -37,6 +37,9 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
+#ifndef S1_UPDATE_ALL
+#define S1_UPDATE_ALL 1  // (measured on 16384^2: 3.06 -> 3.00 ms idle, 3.17 -> 3.12 ms with the drag; 0 = every lane tests whether its particle exists first)
+#endif
 #ifndef S1_UNROLL
 #define S1_UNROLL 1
 #endif
@@ -349,6 +352,23 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                     E[q][p].x = L::get(rw.x, 2 * p), O[q][p].x = L::get(rw.x, 2 * p + 1);
                     E[q][p].y = L::get(rw.y, 2 * p), O[q][p].y = L::get(rw.y, 2 * p + 1);
                     fe[q][p] = (rw.fl >> (16 * p)) & 0xffu, fo[q][p] = (rw.fl >> (16 * p + 8)) & 0xffu;
+#if S1_UPDATE_ALL
+                    {   // every lane runs the rule, also on the zeros of particles that do not exist (rows past the chunk, row
+                        // padding); those are put back to zeros — coordinates and flag byte — in a block only the warps at
+                        // the cloth's right and lower edge enter, so no merge of two register sets precedes the sticks
+                        const uint32_t fe_in = fe[q][p], fo_in = fo[q][p];
+                        T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
+                        particle_update(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u);
+                        particle_update(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u);
+                        const bool ok_e = row_ok && (NP == 1 || ce + 2 * p < g.nx), ok_o = row_ok && ce + 2 * p + 1 < g.nx;
+                        if (!__all_sync(FULL, ok_o)) {  // (ok_o implies ok_e)
+                            if (!ok_e) E[q][p].x = E[q][p].y = px0 = py0 = T(0), fe[q][p] = 0;
+                            if (!ok_o) O[q][p].x = O[q][p].y = px1 = py1 = T(0), fo[q][p] = 0;
+                        }
+                        L::set(vpx[q], 2 * p, px0), L::set(vpx[q], 2 * p + 1, px1), L::set(vpy[q], 2 * p, py0), L::set(vpy[q], 2 * p + 1, py1);
+                        if (counted) events.note2(fe_in, fe[q][p], fo_in, fo[q][p]);
+                    }
+#else
                     if (row_ok) {
                         const uint32_t fe_in = fe[q][p], fo_in = fo[q][p];
                         T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
@@ -357,6 +377,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                         L::set(vpx[q], 2 * p, px0), L::set(vpx[q], 2 * p + 1, px1), L::set(vpy[q], 2 * p, py0), L::set(vpy[q], 2 * p + 1, py1);
                         if (counted) events.note2(fe_in, fe[q][p], fo_in, fo[q][p]);
                     }
+#endif
                 }
             }
         } else {
