@@ -37,6 +37,9 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
+#ifndef S1_LATE_CLAMP
+#define S1_LATE_CLAMP 1  // (measured on 16384^2: 3.10 -> 3.07 ms idle, 3.23 -> 3.19 ms with the drag; 4096^2 0.2177 -> 0.2139 ms)
+#endif
 #ifndef S1_UPDATE_ALL
 #define S1_UPDATE_ALL 1  // (measured on 16384^2: 3.06 -> 3.00 ms idle, 3.17 -> 3.12 ms with the drag; 0 = every lane tests whether its particle exists first)
 #endif
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         // ---- the trip (particle_update_common); if any lane of the warp has a pinned particle, one within the mouse's reach
         // ---- or one leaving the window — rare — the rule itself re-runs on the kept inputs.  Otherwise: the rule itself.
         VL vpx[2], vpy[2];
+        bool clamp_e[2][NP] = {}, clamp_o[2][NP] = {};  // S1_LATE_CLAMP: particles that left the window in this trip
         bool rare = !kCommonFirst;
         if (kCommonFirst) {
 #pragma unroll
@@ -358,9 +362,10 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                         // the cloth's right and lower edge enter, so no merge of two register sets precedes the sticks
                         const uint32_t fe_in = fe[q][p], fo_in = fo[q][p];
                         T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
-                        particle_update(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u);
-                        particle_update(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u);
                         const bool ok_e = row_ok && (NP == 1 || ce + 2 * p < g.nx), ok_o = row_ok && ce + 2 * p + 1 < g.nx;
+                        // (the window clamp — an event — is applied to the whole trip below, behind one vote)
+                        clamp_e[q][p] = particle_update<T, !S1_LATE_CLAMP>(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u) && ok_e;
+                        clamp_o[q][p] = particle_update<T, !S1_LATE_CLAMP>(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u) && ok_o;
                         if (!__all_sync(FULL, ok_o)) {  // (ok_o implies ok_e)
                             if (!ok_e) E[q][p].x = E[q][p].y = px0 = py0 = T(0), fe[q][p] = 0;
                             if (!ok_o) O[q][p].x = O[q][p].y = px1 = py1 = T(0), fo[q][p] = 0;
@@ -380,6 +385,26 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
 #endif
                 }
             }
+#if S1_UPDATE_ALL && S1_LATE_CLAMP
+            {
+                bool any_clamp = false;
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) any_clamp |= clamp_e[q][p] | clamp_o[q][p];
+                if (__any_sync(FULL, any_clamp)) {  // a particle of the trip left the window (:164-178)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
+                            if (clamp_e[q][p]) particle_window_clamp(E[q][p].x, E[q][p].y, px0, py0, u);
+                            if (clamp_o[q][p]) particle_window_clamp(O[q][p].x, O[q][p].y, px1, py1, u);
+                            L::set(vpx[q], 2 * p, px0), L::set(vpx[q], 2 * p + 1, px1), L::set(vpy[q], 2 * p, py0), L::set(vpy[q], 2 * p + 1, py1);
+                        }
+                }
+            }
+#endif
         } else {
             // the common case wrote every lane, also the particles that do not exist (zero-filled rows past the chunk, the
             // row padding): back to the zeros they were loaded as (their flag bytes are zero either way)

@@ -255,14 +255,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 // (*particle).update, physics/particle.go:75-181.  `fl` is the particle's flag byte.
+// The window clamp at the end of the rule, :164-178.
 template <typename T>
-__device__ __forceinline__ void particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,
+__device__ __forceinline__ void particle_window_clamp(T& x, T& y, T& px, T& py, const FrameU<T>& u) {
+    if (x >= u.W) {  // :164-170
+        x = u.W;
+        px = x;
+    } else if (x < T(0)) {
+        x = T(0);
+        px = x;
+    }
+    if (y > u.H) {  // :172-178
+        y = u.H;
+        py = y;
+    } else if (y < T(0)) {
+        y = T(0);
+        py = y;
+    }
+}
+
+// CLAMP = false leaves the window clamp to the caller: the return value says whether particle_window_clamp still has to
+// run on this particle (it left the window — an event; a caller can test a whole warp's particles with one vote and keep
+// the clamp's selects and copies out of its common path).  CLAMP = true: the whole rule, returns false.
+template <typename T, bool CLAMP = true>
+__device__ __forceinline__ bool particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,
                                                 const FrameU<T>& u) {
     fl &= ~(uint32_t)CLOTHGPU_FLAG_HIGHLIGHT;  // :76
     if (fl & CLOTHGPU_FLAG_PIN) {              // :85-92
         x += u.off_x;
         y += u.off_y;
-        return;
+        return false;
     }
     const T dx = x - u.mx;  // :104-106; the sqrt is folded into the thresholds s_*
     const T dy = y - u.my;
@@ -281,20 +303,9 @@ __device__ __forceinline__ void particle_update(T& x, T& y, T& px, T& py, uint32
     y = y + (y - py) * u.fric + u.gy;    // :160
     px = ox;                             // :162
     py = oy;
-    if (x >= u.W) {  // :164-170
-        x = u.W;
-        px = x;
-    } else if (x < T(0)) {
-        x = T(0);
-        px = x;
-    }
-    if (y > u.H) {  // :172-178
-        y = u.H;
-        py = y;
-    } else if (y < T(0)) {
-        y = T(0);
-        py = y;
-    }
+    if (!CLAMP) return !(x < u.W) || x < T(0) || !(y <= u.H) || y < T(0);
+    particle_window_clamp(x, y, px, py, u);
+    return false;
 }
 
 // The common case of particle_update — not pinned, out of the mouse's reach, still inside the window after the step —
