@@ -37,6 +37,9 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
+#ifndef S1_PIN_VOTE
+#define S1_PIN_VOTE 2  // 0: never, 1: every instantiation, 2: frames with a drag only
+#endif
 #ifndef S1_LATE_CLAMP
 #define S1_LATE_CLAMP 1  // (measured on 16384^2: 3.10 -> 3.07 ms idle, 3.23 -> 3.19 ms with the drag; 4096^2 0.2177 -> 0.2139 ms)
 #endif
@@ -345,6 +348,8 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
         }
         }
         if (!kCommonFirst || __any_sync(FULL, rare)) {
+            auto update_rows = [&](auto may_pin) {
+            constexpr bool kMayPin = decltype(may_pin)::value;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const RowRaw<T> rw = fetch_row(q);  // the kept inputs
@@ -364,8 +369,10 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                         T px0 = L::get(vpx[q], 2 * p), px1 = L::get(vpx[q], 2 * p + 1), py0 = L::get(vpy[q], 2 * p), py1 = L::get(vpy[q], 2 * p + 1);
                         const bool ok_e = row_ok && (NP == 1 || ce + 2 * p < g.nx), ok_o = row_ok && ce + 2 * p + 1 < g.nx;
                         // (the window clamp — an event — is applied to the whole trip below, behind one vote)
-                        clamp_e[q][p] = particle_update<T, !S1_LATE_CLAMP>(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u) && ok_e;
-                        clamp_o[q][p] = particle_update<T, !S1_LATE_CLAMP>(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u) && ok_o;
+                        // (a vote on "the mouse is near one of the warp's particles" in front of :108-149 as well measured
+                        //  3.00 vs 3.02 ms on 16384^2 but 0.218 vs 0.215 ms on 4096^2 with a drag: not taken)
+                        clamp_e[q][p] = particle_update<T, !S1_LATE_CLAMP, kMayPin>(E[q][p].x, E[q][p].y, px0, py0, fe[q][p], u) && ok_e;
+                        clamp_o[q][p] = particle_update<T, !S1_LATE_CLAMP, kMayPin>(O[q][p].x, O[q][p].y, px1, py1, fo[q][p], u) && ok_o;
                         if (!__all_sync(FULL, ok_o)) {  // (ok_o implies ok_e)
                             if (!ok_e) E[q][p].x = E[q][p].y = px0 = py0 = T(0), fe[q][p] = 0;
                             if (!ok_o) O[q][p].x = O[q][p].y = px1 = py1 = T(0), fo[q][p] = 0;
@@ -385,6 +392,13 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
 #endif
                 }
             }
+            };
+            // pins are the cloth's top row and what ctrl-clicks add: one vote over the trip's flag bytes decides whether the
+            // rule runs with or without its pinned branch.  Measured per instantiation (16384^2 / 4096^2): with a drag 3.22 ->
+            // 3.14-3.19 ms / 0.2235 -> 0.2170 ms, without one 3.08 -> 3.07-3.11 ms / 0.2142 -> 0.2206 ms — so only there.
+            constexpr bool kPinVote = S1_UPDATE_ALL && (S1_PIN_VOTE == 1 || (S1_PIN_VOTE == 2 && DRAG));
+            if (kPinVote && !__any_sync(FULL, ((fl_q[0] | fl_q[1]) & (CLOTHGPU_FLAG_PIN * 0x01010101u)) != 0u)) update_rows(std::false_type{});
+            else update_rows(std::true_type{});
 #if S1_UPDATE_ALL && S1_LATE_CLAMP
             {
                 bool any_clamp = false;

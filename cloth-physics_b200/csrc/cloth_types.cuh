@@ -254,7 +254,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 }
 
-// (*particle).update, physics/particle.go:75-181.  `fl` is the particle's flag byte.
+// ---- (*particle).update, physics/particle.go:75-181, in pieces; `fl` is the particle's flag byte ----
 // The window clamp at the end of the rule, :164-178.
 template <typename T>
 __device__ __forceinline__ void particle_window_clamp(T& x, T& y, T& px, T& py, const FrameU<T>& u) {
@@ -274,21 +274,17 @@ __device__ __forceinline__ void particle_window_clamp(T& x, T& y, T& px, T& py, 
     }
 }
 
-// CLAMP = false leaves the window clamp to the caller: the return value says whether particle_window_clamp still has to
-// run on this particle (it left the window — an event; a caller can test a whole warp's particles with one vote and keep
-// the clamp's selects and copies out of its common path).  CLAMP = true: the whole rule, returns false.
-template <typename T, bool CLAMP = true>
-__device__ __forceinline__ bool particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,
-                                                const FrameU<T>& u) {
-    fl &= ~(uint32_t)CLOTHGPU_FLAG_HIGHLIGHT;  // :76
-    if (fl & CLOTHGPU_FLAG_PIN) {              // :85-92
-        x += u.off_x;
-        y += u.off_y;
-        return false;
-    }
-    const T dx = x - u.mx;  // :104-106; the sqrt is folded into the thresholds s_*
+// The pieces of the rule after the pinned test, so that a caller can put votes between them (cloth_stream1.cuh):
+// squared distance to the mouse (:104-106; the sqrt is folded into the thresholds s_*) ...
+template <typename T>
+__device__ __forceinline__ T particle_mouse_dist2(const T x, const T y, const FrameU<T>& u) {
+    const T dx = x - u.mx;
     const T dy = y - u.my;
-    const T s = dx * dx + dy * dy;
+    return dx * dx + dy * dy;
+}
+// ... what the mouse does to a particle at squared distance s (:108-149; nothing when s >= u.s_near) ...
+template <typename T>
+__device__ __forceinline__ void particle_mouse(const T x, const T y, T& px, T& py, uint32_t& fl, const T s, const FrameU<T>& u) {
     if ((u.buttons & CLOTHGPU_MOUSE_DRAGGING) && s < u.s_drag) {  // :108-125
         px = x - u.push_x;
         py = y - u.push_y;
@@ -298,6 +294,12 @@ __device__ __forceinline__ bool particle_update(T& x, T& y, T& px, T& py, uint32
         fl |= CLOTHGPU_FLAG_HIGHLIGHT;
         if (u.buttons & CLOTHGPU_MOUSE_RIGHT) fl &= ~(uint32_t)CLOTHGPU_FLAG_ACTIVE;
     }
+}
+// ... and the Verlet step (:151-162) with the window clamp (:164-178).  CLAMP = false leaves the clamp to the caller: the
+// return value says whether particle_window_clamp still has to run on this particle (it left the window — an event; a
+// caller can test a whole warp's particles with one vote and keep the clamp's selects and copies out of its common path).
+template <typename T, bool CLAMP>
+__device__ __forceinline__ bool particle_integrate(T& x, T& y, T& px, T& py, const FrameU<T>& u) {
     const T ox = x, oy = y;              // :151
     x = x + (x - px) * u.fric + u.gx;    // :159
     y = y + (y - py) * u.fric + u.gy;    // :160
@@ -306,6 +308,22 @@ __device__ __forceinline__ bool particle_update(T& x, T& y, T& px, T& py, uint32
     if (!CLAMP) return !(x < u.W) || x < T(0) || !(y <= u.H) || y < T(0);
     particle_window_clamp(x, y, px, py, u);
     return false;
+}
+
+// (*particle).update, physics/particle.go:75-181.  CLAMP as in particle_integrate (true: the whole rule, returns false).
+// MAY_PIN = false: the caller knows that the particle is not pinned (it has looked at the flag bytes of a whole warp's
+// particles at once), so the early return — and the merge of two register sets behind it — is not compiled in.
+template <typename T, bool CLAMP = true, bool MAY_PIN = true>
+__device__ __forceinline__ bool particle_update(T& x, T& y, T& px, T& py, uint32_t& fl,
+                                                const FrameU<T>& u) {
+    fl &= ~(uint32_t)CLOTHGPU_FLAG_HIGHLIGHT;  // :76
+    if (MAY_PIN && (fl & CLOTHGPU_FLAG_PIN)) {  // :85-92
+        x += u.off_x;
+        y += u.off_y;
+        return false;
+    }
+    particle_mouse(x, y, px, py, fl, particle_mouse_dist2(x, y, u), u);
+    return particle_integrate<T, CLAMP>(x, y, px, py, u);
 }
 
 // The common case of particle_update — not pinned, out of the mouse's reach, still inside the window after the step —
