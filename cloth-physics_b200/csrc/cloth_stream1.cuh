@@ -37,6 +37,9 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
+#ifndef S1_F32_COMMON_FIRST
+#define S1_F32_COMMON_FIRST 1  // (binary32 takes the branch-free common case first: 2.10 vs 2.31 ms idle, 2.23 vs 2.34 ms with a drag on 16384^2)
+#endif
 #ifndef S1_PIN_VOTE
 #define S1_PIN_VOTE 2  // 0: never, 1: every instantiation, 2: frames with a drag only
 #endif
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
     // binary32, whose launch is bound by issue slots — and -20 % to -32 % in binary64 (3.88 / 4.17 vs 3.15-3.19 ms on
     // 16384^2 with the slots refilled after / before the arithmetic): keeping the inputs for the rare path costs 16
     // registers the binary64 kernel does not have (88 bytes of spills in the loop).  So: binary32 only.
-    constexpr bool kCommonFirst = sizeof(T) == 4;
+    constexpr bool kCommonFirst = S1_F32_COMMON_FIRST && (sizeof(T) == 4);
     constexpr bool kEarlyRefill = sizeof(T) == 8;  // binary64: a trip's slots are refilled before its arithmetic
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;

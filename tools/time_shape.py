@@ -12,7 +12,8 @@ from clothgpu import _abi  # noqa: E402
 
 nx, ny, K = (int(a) for a in sys.argv[1:4])
 frames = int(sys.argv[4]) if len(sys.argv) > 4 else 50
-cloth = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K))
+prec = _abi.F32 if os.environ.get("CLOTH_F32") else _abi.F64   # CLOTH_F32=1: the binary32 mode
+cloth = clothgpu.Cloth(_abi.grid_desc(nx, ny, pin_rule=_abi.PIN_TOP_ROW, max_iterations=K, precision=prec))
 if len(sys.argv) > 5:
     cloth.set_schedule(getattr(_abi, "SCHED_" + sys.argv[5].upper()))
 f = _abi.default_frame(K)
