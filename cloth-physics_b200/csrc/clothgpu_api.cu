@@ -1253,9 +1253,10 @@ int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* act
 }
 
 namespace {
-// Live-stick export on the handle's stream: ONE launch (per-block counts, decoupled look-back, ballot-ranked scatter) into
-// c->seg_out.  quads = false: float4 endpoints at [0, n), optional uint2 indices behind them; quads = true: 2 float4 of
-// outline per stick.  Highlight bytes behind the 32 B/stick area in both cases.
+// Live-stick export on the handle's stream: a flags-only plan launch + the export launch (cloth_kernels.cuh; ONE launch for
+// cloths of a few tiles) into c->seg_out — or, with `direct`, straight into the caller's pinned host memory.
+// quads = false: float4 endpoints at [0, n), optional uint2 indices behind them; quads = true: 2 float4 of
+// outline per stick.
 // Where an export goes when not into the handle's own device buffer: device-visible addresses of the caller's pinned host
 // memory (null = the handle's buffer), the list's capacity there, and where its length is to be written.
 struct ExportTarget {
