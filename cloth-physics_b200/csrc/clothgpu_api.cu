@@ -1253,10 +1253,6 @@ int clothgpu_read_masks(clothgpu* c, int32_t cloth, uint32_t* pin, uint32_t* act
 }
 
 namespace {
-// Live-stick export on the handle's stream: a flags-only plan launch + the export launch (cloth_kernels.cuh; ONE launch for
-// cloths of a few tiles) into c->seg_out — or, with `direct`, straight into the caller's pinned host memory.
-// quads = false: float4 endpoints at [0, n), optional uint2 indices behind them; quads = true: 2 float4 of
-// outline per stick.
 // Where an export goes when not into the handle's own device buffer: device-visible addresses of the caller's pinned host
 // memory (null = the handle's buffer), the list's capacity there, and where its length is to be written.
 struct ExportTarget {
@@ -1266,6 +1262,10 @@ struct ExportTarget {
     unsigned long long* total = nullptr;
     size_t cap = 0;
 };
+// Live-stick export on the handle's stream: a flags-only plan launch + the export launch (cloth_kernels.cuh; ONE launch for
+// cloths of a few tiles) into c->seg_out — or, with `direct`, straight into the caller's pinned host memory.
+// quads = false: float4 endpoints at [0, n), optional uint2 indices behind them; quads = true: 2 float4 of
+// outline per stick.  Highlight bytes behind the 32 B/stick area in both cases.
 int compact_enqueue(clothgpu* c, int32_t cloth, bool with_idx, bool quads, float line_width, size_t* max_sticks_out,
                     const ExportTarget* direct = nullptr) {
     if (cloth < 0 || cloth >= c->g.ensemble) return fail(CLOTHGPU_ERR_INVALID, "cloth %d out of range", cloth);
