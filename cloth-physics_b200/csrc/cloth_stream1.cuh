@@ -37,6 +37,10 @@ namespace clothgpu_impl {
 #define S1_RING_CTAS 5
 #endif
 constexpr int kS1Threads = 128;       // 4 independent warps per CTA
+#ifndef S1_PINS_KNOWN
+#define S1_PINS_KNOWN 0  // 1: one vote per trip instead of one per pass on "is any endpoint pinned" — measured 3.11 -> 3.07 ms with
+#endif                   // a drag but 3.05 -> 3.07 ms idle on 16384^2, and 0.2167 -> 0.2236 ms idle on 4096^2: not taken
+constexpr int kS1Pins = S1_PINS_KNOWN ? kPinsKnown : kPinsVote;
 #ifndef S1_F32_COMMON_FIRST
 #define S1_F32_COMMON_FIRST 1  // (binary32 takes the branch-free common case first: 2.10 vs 2.31 ms idle, 2.23 vs 2.34 ms with a drag on 16384^2)
 #endif
@@ -449,6 +453,16 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
             if (r + q < re && ex_e) store_prev(r + q, vpx[q], vpy[q]);
         const bool own_r[2] = {r >= ra && r < rb, r + 1 >= ra && r + 1 < rb};
         bool touched = false;
+        // pins are the cloth's top row and what ctrl-clicks add: ONE vote per trip over every particle its four passes can
+        // touch (the two rows, the row carried over from the trip before; a neighbouring lane's particle is some lane's
+        // own) tells the passes whether any of them needs per-endpoint multipliers (constraint.go:46-53)
+        bool trip_pins = true;
+        if (kS1Pins == kPinsKnown) {
+            uint32_t any_flag = 0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) any_flag |= fe[0][p] | fo[0][p] | fe[1][p] | fo[1][p] | cfe[p] | cfo[p];
+            trip_pins = __any_sync(FULL, (any_flag & CLOTHGPU_FLAG_PIN) != 0u);
+        }
 #if defined(S1_NO_MATH)  // timing experiment only: what the memory system gives this access pattern without the sticks
         if (u.iterations == 12345)
 #endif
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                     live |= live_of(fe[q][p], fo[q][p], CLOTHGPU_FLAG_ALIVE_H) << k;
                     pins |= ((fe[q][p] & CLOTHGPU_FLAG_PIN) | ((fo[q][p] & CLOTHGPU_FLAG_PIN) << 1)) << (2 * k);
                 }
-            const uint32_t tore = relax_n<T, DRAG, 2 * NP>(hh, tt, live, pins, u, dragging, touched);
+            const uint32_t tore = relax_n<T, DRAG, 2 * NP, kS1Pins>(hh, tt, live, pins, u, dragging, touched, 0xffffffffu, trip_pins);
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -499,7 +513,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                     if (!cross || lane < 31) live |= live_of(fo[q][p], ftail, CLOTHGPU_FLAG_ALIVE_H) << k;
                     pins |= ((fo[q][p] & CLOTHGPU_FLAG_PIN) | ((ftail & CLOTHGPU_FLAG_PIN) << 1)) << (2 * k);
                 }
-            const uint32_t tore = relax_n<T, DRAG, 2 * NP>(hh, tt, live, pins, u, dragging, touched);
+            const uint32_t tore = relax_n<T, DRAG, 2 * NP, kS1Pins>(hh, tt, live, pins, u, dragging, touched, 0xffffffffu, trip_pins);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
 #pragma unroll
@@ -523,7 +537,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                 pins |= ((fe[0][p] & CLOTHGPU_FLAG_PIN) | ((fe[1][p] & CLOTHGPU_FLAG_PIN) << 1) | ((fo[0][p] & CLOTHGPU_FLAG_PIN) << 2) |
                          ((fo[1][p] & CLOTHGPU_FLAG_PIN) << 3)) << (4 * p);
             }
-            const uint32_t tore = relax_n<T, DRAG, NC>(hh, tt, live, pins, u, dragging, touched);
+            const uint32_t tore = relax_n<T, DRAG, NC, kS1Pins>(hh, tt, live, pins, u, dragging, touched, 0xffffffffu, trip_pins);
             if (own_cols && own_r[0]) visits += __popc(live), torn += __popc(tore);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
@@ -542,7 +556,7 @@ __global__ void __launch_bounds__(kS1Threads, RING ? S1_RING_CTAS : S1_MIN_CTAS)
                 pins |= ((cfe[p] & CLOTHGPU_FLAG_PIN) | ((fe[0][p] & CLOTHGPU_FLAG_PIN) << 1) | ((cfo[p] & CLOTHGPU_FLAG_PIN) << 2) |
                          ((fo[0][p] & CLOTHGPU_FLAG_PIN) << 3)) << (4 * p);
             }
-            const uint32_t tore = relax_n<T, DRAG, NC>(hh, tt, live, pins, u, dragging, touched);
+            const uint32_t tore = relax_n<T, DRAG, NC, kS1Pins>(hh, tt, live, pins, u, dragging, touched, 0xffffffffu, trip_pins);
             if (own_cols && r - 1 >= ra && r - 1 < rb) visits += __popc(live), torn += __popc(tore);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
